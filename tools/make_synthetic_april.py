@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""Write a synthetic `.april` model (random, calibrated weights) laid out exactly as
+/root/reference/extra/export-april.py:374-443 does: "APRILMDL", u32 version=1, u64 header_size,
+header{lang[8], name, desc, u32 kind=1, params entry, u64 3, 3 x network entry}, encoder.onnx,
+decoder.onnx, joiner.onnx, params (params DIRECTLY after network[2]: april_model.c:61 reads
+params without seeking). The three ONNX graphs mimic a torch 1.13 / opset-11 export of
+MergedEncoder / MergedDecoder / Joiner (export-april.py:183-223,289-331) for icefall
+lstm_transducer_stateless2 [external] — no real model file exists in this image, so
+every run of the reference/oracle/engine here is on synthetic weights.
+
+Test / bench fixture generator — not product code.
+"""
+import argparse
+import os
+import struct
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import np_ref  # noqa: E402
+import onnx_lite as ox  # noqa: E402
+from gen_pcm import gen_stream  # noqa: E402
+
+FULL = dict(L=12, D=512, H=1024, F=2048, J=512, E=512, V=500, CTX=2, MEL=80, SEG=9, STEP=4)
+TINY = dict(L=2, D=64, H=128, F=256, J=64, E=64, V=64, CTX=2, MEL=80, SEG=9, STEP=4)
+MID = dict(L=3, D=128, H=256, F=512, J=128, E=128, V=200, CTX=2, MEL=80, SEG=9, STEP=4)
+PRESETS = dict(full=FULL, tiny=TINY, mid=MID)
+
+
+# ----------------------------------------------------------------------------- vocabulary
+def make_vocab(V, rs):
+    """V pieces; id0 = <blk>; includes '.', ',', '?', '!', digit pieces, ' '-prefixed pieces so every
+    greedy heuristic of april_session.c:338-358,369-388 is reachable."""
+    toks = ["<blk>", "<sos/eos>", "<unk>", ".", ",", "?", "!"]
+    toks += [str(d) for d in range(10)]
+    toks += [" " + str(d) for d in range(1, 6)]
+    cons, vow = "BCDFGHJKLMNPRSTVWZ", "AEIOU"
+    seen = set(toks)
+    while len(toks) < V:
+        n = 1 + int(rs.randint(0, 3))
+        s = ""
+        for _ in range(n):
+            s += cons[rs.randint(len(cons))] + vow[rs.randint(len(vow))]
+        if rs.rand() < 0.3:
+            s = s[:-1]
+        if rs.rand() < 0.45:
+            s = " " + s
+        if s and s not in seen:
+            seen.add(s)
+            toks.append(s)
+    return toks[:V]
+
+
+# ----------------------------------------------------------------------------- weights
+def make_weights(d, seed):
+    rs = np.random.RandomState(seed)
+    f = np.float32
+
+    def rnd(*shape, std):
+        return (rs.randn(*shape) * std).astype(f)
+
+    W = {}
+    W["conv1_w"], W["conv1_b"] = rnd(8, 1, 3, 3, std=0.15), rnd(8, std=0.3)
+    W["conv2_w"], W["conv2_b"] = rnd(32, 8, 3, 3, std=0.25), rnd(32, std=0.3)
+    W["conv3_w"], W["conv3_b"] = rnd(128, 32, 3, 3, std=0.12), rnd(128, std=0.3)
+    f3 = ((d["MEL"] - 3) // 2 - 1) // 2
+    W["out_w"], W["out_b"] = rnd(d["D"], 128 * f3, std=1.0 / np.sqrt(128 * f3)), rnd(d["D"], std=0.1)
+    W["out_norm_eps"] = f(0.25)
+    D, H, F = d["D"], d["H"], d["F"]
+    for l in range(d["L"]):
+        p = "l%d_" % l
+        W[p + "w_ih"], W[p + "b_ih"] = rnd(4 * H, D, std=1.0 / np.sqrt(D)), rnd(4 * H, std=0.2)
+        W[p + "w_hh"], W[p + "b_hh"] = rnd(4 * H, D, std=1.3 / np.sqrt(D)), rnd(4 * H, std=0.2)
+        W[p + "b_ih"][H:2 * H] += 0.5                                   # forget-gate bias: bounded memory
+        W[p + "w_hr"] = rnd(D, H, std=1.5 / np.sqrt(H))
+        W[p + "ff1_w"], W[p + "ff1_b"] = rnd(F, D, std=1.2 / np.sqrt(D)), rnd(F, std=0.2)
+        W[p + "ff2_w"], W[p + "ff2_b"] = rnd(D, F, std=0.7 / np.sqrt(F)), rnd(D, std=0.05)
+        W[p + "norm_eps"] = f(np.exp(-1.5 + 0.3 * rs.randn()))
+    W["enc_proj_w"], W["enc_proj_b"] = rnd(d["J"], D, std=1.0 / np.sqrt(D)), rnd(d["J"], std=0.1)
+    W["emb"] = rnd(d["V"], d["E"], std=1.0)
+    W["dec_conv_w"] = rnd(d["E"], 1, d["CTX"], std=0.7)
+    W["dec_proj_w"], W["dec_proj_b"] = rnd(d["J"], d["E"], std=0.8 / np.sqrt(d["E"])), rnd(d["J"], std=0.1)
+    W["join_w"], W["join_b"] = rnd(d["V"], d["J"], std=3.0 / np.sqrt(d["J"])), rnd(d["V"], std=0.3)
+    return W
+
+
+def calibrate(W, d, vocab, seed):
+    """Shape the joiner's blank row so that (i) silence -> confidently blank (so the 2200 ms path
+    fires), (ii) noisy audio -> a healthy mix of blank / non-blank, (iii) punctuation and digit
+    pieces win now and then. Pure fixture tuning; changes nothing about the arithmetic."""
+    NS, SECS = 16, 6
+    segs = [np_ref.segments(np_ref.fbank_rows_fast(gen_stream(10_000 + seed + i, 16000 * SECS))) for i in range(NS)]
+    seg = np.stack(segs, axis=1)                       # [T, NS, 9, 80]
+    T = seg.shape[0]
+    h = np.zeros((d["L"], NS, d["D"]), np.float32)
+    c = np.zeros((d["L"], NS, d["H"]), np.float32)
+    eo = np.zeros((T, NS, d["J"]), np.float32)
+    for t in range(T):
+        eo[t], h, c = np_ref.encoder_step(W, seg[t], h, c)
+    eo = eo.reshape(T * NS, -1)
+    energy = seg.mean(axis=(2, 3)).reshape(-1)
+    n = T * NS
+    sil = energy < -12.0
+    if sil.sum() < 4 or (~sil).sum() < 4:
+        sil = energy < np.median(energy)
+    loud0 = energy > -3.0
+    ctx = np.zeros((n, 2), np.int64)
+    do = np_ref.decoder(W, ctx)
+    t_in = np.tanh(eo + do)
+    u = t_in[sil].mean(0) - t_in[loud0 if loud0.sum() >= 8 else ~sil].mean(0)
+    u /= (np.linalg.norm(u) + 1e-9)
+    W["join_w"][0] = 0.0
+    W["join_b"][0] = 0.0
+    # boost punctuation / digits a little so their heuristics are exercised
+    for i, tk in enumerate(vocab):
+        if tk in (".", ",", "?", "!"):
+            W["join_b"][i] += 1.0
+        elif tk.strip().isdigit():
+            W["join_b"][i] += 0.3
+    W["join_b"][1] = -30.0
+    W["join_b"][2] = -30.0
+    logits = np_ref.joiner(W, eo, do)
+    mx = logits[:, 1:].max(1)
+    proj = t_in @ u
+    delta = proj[sil].mean() - proj[~sil].mean()
+    gamma = 9.0 / max(delta, 1e-3)
+    # speech: ~45 % of steps emit on the first pass (early_emit = 1, april_session.c:449-453)
+    loud = energy > -3.0
+    if loud.sum() < 8:
+        loud = ~sil
+    b = np.quantile(mx[loud] + 1.0 - gamma * proj[loud], 0.25)
+    W["join_w"][0] = (gamma * u).astype(np.float32)
+    W["join_b"][0] = np.float32(b)
+    return W
+
+
+# ----------------------------------------------------------------------------- ONNX graphs
+def _double_swish(g, x):
+    one = g.const(np.array(1.0, np.float32))
+    s = g.op("Sub", [x, one])
+    s = g.op("Sigmoid", [s])
+    return g.op("Mul", [x, s])
+
+
+def _basic_norm(g, x, eps):
+    two = g.const(np.array(2.0, np.float32))
+    p = g.op("Pow", [x, two])
+    m = g.op("ReduceMean", [p], axes=[-1], keepdims=1)
+    e = g.const(np.array(eps, np.float32))
+    a = g.op("Add", [m, e])
+    mh = g.const(np.array(-0.5, np.float32))
+    s = g.op("Pow", [a, mh])
+    return g.op("Mul", [x, s])
+
+
+def _linear3d(g, x, w, b):
+    """nn.Linear on a 3-D tensor -> MatMul(x, W^T const) + Add(bias) (torch exporter convention)."""
+    wt = g.init(np.ascontiguousarray(w.T), g.fresh("onnx::MatMul"))
+    y = g.op("MatMul", [x, wt])
+    if b is None:
+        return y
+    return g.op("Add", [g.init(b, g.fresh("bias")), y])
+
+
+def build_encoder(W, d):
+    g = ox.GraphBuilder("torch_jit")
+    L, D, H = d["L"], d["D"], d["H"]
+    g.add_input("x", ox.FLOAT, [1, d["SEG"], d["MEL"]])
+    g.add_input("h", ox.FLOAT, [L, 1, D])
+    g.add_input("c", ox.FLOAT, [L, 1, H])
+    x = g.op("Unsqueeze", ["x"], axes=[1])
+    for i, stride in ((1, 1), (2, 2), (3, 2)):
+        w = g.init(W["conv%d_w" % i], "encoder.encoder_embed.conv.%d.weight" % ((i - 1) * 3))
+        b = g.init(W["conv%d_b" % i], "encoder.encoder_embed.conv.%d.bias" % ((i - 1) * 3))
+        x = g.op("Conv", [x, w, b], dilations=[1, 1], group=1, kernel_shape=[3, 3],
+                 pads=[0, 0, 0, 0], strides=[stride, stride])
+        x = _double_swish(g, x)
+    x = g.op("Transpose", [x], perm=[0, 2, 1, 3])
+    f3 = ((d["MEL"] - 3) // 2 - 1) // 2
+    shp = g.const(np.array([1, 1, 128 * f3], np.int64))
+    x = g.op("Reshape", [x, shp])
+    x = _linear3d(g, x, W["out_w"], W["out_b"])
+    x = _basic_norm(g, x, float(W["out_norm_eps"]))
+    x = g.op("Transpose", [x], perm=[1, 0, 2])                       # (T=1, N=1, D)
+    hs, cs = [], []
+    for l in range(L):
+        p = "l%d_" % l
+        st, en, ax = (g.const(np.array([l], np.int64)), g.const(np.array([l + 1], np.int64)),
+                      g.const(np.array([0], np.int64)))
+        hl = g.op("Slice", ["h", st, en, ax])
+        st, en, ax = (g.const(np.array([l], np.int64)), g.const(np.array([l + 1], np.int64)),
+                      g.const(np.array([0], np.int64)))
+        cl = g.op("Slice", ["c", st, en, ax])
+        h2 = g.op("Squeeze", [hl], axes=[0])                         # (1, D)
+        c2 = g.op("Squeeze", [cl], axes=[0])                         # (1, H)
+        x2 = g.op("Squeeze", [x], axes=[0])                          # (1, D)
+        wih = g.init(W[p + "w_ih"], "encoder.encoder.layers.%d.lstm.weight_ih_l0" % l)
+        bih = g.init(W[p + "b_ih"], "encoder.encoder.layers.%d.lstm.bias_ih_l0" % l)
+        whh = g.init(W[p + "w_hh"], "encoder.encoder.layers.%d.lstm.weight_hh_l0" % l)
+        bhh = g.init(W[p + "b_hh"], "encoder.encoder.layers.%d.lstm.bias_hh_l0" % l)
+        gi = g.op("Gemm", [x2, wih, bih], alpha=1.0, beta=1.0, transB=1)
+        gh = g.op("Gemm", [h2, whh, bhh], alpha=1.0, beta=1.0, transB=1)
+        gates = g.op("Add", [gi, gh])
+        i_, f_, g_, o_ = g.op("Split", [gates], n_out=4, axis=1, split=[H, H, H, H])
+        i_ = g.op("Sigmoid", [i_])
+        f_ = g.op("Sigmoid", [f_])
+        g_ = g.op("Tanh", [g_])
+        o_ = g.op("Sigmoid", [o_])
+        cn = g.op("Add", [g.op("Mul", [f_, c2]), g.op("Mul", [i_, g_])])
+        m = g.op("Mul", [o_, g.op("Tanh", [cn])])
+        whr = g.init(np.ascontiguousarray(W[p + "w_hr"].T), g.fresh("onnx::MatMul"))
+        hn = g.op("MatMul", [m, whr])                                # (1, D)
+        hs.append(g.op("Unsqueeze", [hn], axes=[0]))
+        cs.append(g.op("Unsqueeze", [cn], axes=[0]))
+        x = g.op("Add", [hs[-1], x])                                 # src = dropout(src_lstm) + src
+        ff = _linear3d(g, x, W[p + "ff1_w"], W[p + "ff1_b"])
+        ff = _double_swish(g, ff)
+        ff = _linear3d(g, ff, W[p + "ff2_w"], W[p + "ff2_b"])
+        x = g.op("Add", [x, ff])
+        x = _basic_norm(g, x, float(W[p + "norm_eps"]))
+    x = g.op("Transpose", [x], perm=[1, 0, 2])
+    x = _linear3d(g, x, W["enc_proj_w"], W["enc_proj_b"])
+    g.op("Identity", [x], out_names=["encoder_out"])
+    g.op("Concat", hs, out_names=["next_h"], axis=0)
+    g.op("Concat", cs, out_names=["next_c"], axis=0)
+    g.add_output("encoder_out", ox.FLOAT, [1, 1, d["J"]])
+    g.add_output("next_h", ox.FLOAT, [L, 1, D])
+    g.add_output("next_c", ox.FLOAT, [L, 1, H])
+    return g.serialize()
+
+
+def build_decoder(W, d):
+    g = ox.GraphBuilder("torch_jit")
+    g.add_input("context", ox.INT64, [1, d["CTX"]])
+    emb = g.init(W["emb"], "decoder.embedding.weight")
+    e = g.op("Gather", [emb, "context"], axis=0)                     # (1, CTX, E)
+    e = g.op("Transpose", [e], perm=[0, 2, 1])                       # (1, E, CTX)
+    cw = g.init(W["dec_conv_w"], "decoder.conv.weight")
+    e = g.op("Conv", [e, cw], dilations=[1], group=d["E"], kernel_shape=[d["CTX"]], pads=[0, 0], strides=[1])
+    e = g.op("Transpose", [e], perm=[0, 2, 1])                       # (1, 1, E)
+    e = g.op("Relu", [e])
+    y = _linear3d(g, e, W["dec_proj_w"], W["dec_proj_b"])
+    g.op("Identity", [y], out_names=["decoder_out"])
+    g.add_output("decoder_out", ox.FLOAT, [1, 1, d["J"]])
+    return g.serialize()
+
+
+def build_joiner(W, d):
+    g = ox.GraphBuilder("torch_jit")
+    g.add_input("encoder_out", ox.FLOAT, [1, 1, d["J"]])
+    g.add_input("decoder_out", ox.FLOAT, [1, 1, d["J"]])
+    s = g.op("Add", ["encoder_out", "decoder_out"])
+    s = g.op("Tanh", [s])
+    y = _linear3d(g, s, W["join_w"], W["join_b"])
+    g.op("Identity", [y], out_names=["logits"])
+    g.add_output("logits", ox.FLOAT, [1, 1, d["V"]])
+    return g.serialize()
+
+
+# ----------------------------------------------------------------------------- container
+def params_block(d, vocab, blank_id=0):
+    b = b"PARAMS\0\0"
+    for v in (1, d["SEG"], d["STEP"], d["MEL"], 16000, 10, 25, 1, 20, 0, 0, len(vocab), blank_id):
+        b += struct.pack("<i", v)
+    for t in vocab:
+        tb = t.encode("utf-8")
+        b += struct.pack("<i", len(tb)) + tb
+    return b
+
+
+def write_april(path, nets, params, name, desc, lang="en-us"):
+    header = lang.encode().ljust(8, b"\0")
+    nb = name.encode()
+    db = desc.encode()
+    header += struct.pack("<Q", len(nb)) + nb + struct.pack("<Q", len(db)) + db
+    header += struct.pack("<i", 1)
+    hdr_len = len(header) + 16 + 8 + 16 * len(nets)
+    base = 8 + 4 + 8 + hdr_len
+    offs, cur = [], base
+    for n in nets:
+        offs.append(cur)
+        cur += len(n)
+    params_off = cur
+    header += struct.pack("<QQ", params_off, len(params))
+    header += struct.pack("<Q", len(nets))
+    for o, n in zip(offs, nets):
+        header += struct.pack("<QQ", o, len(n))
+    assert len(header) == hdr_len
+    with open(path, "wb") as f:
+        f.write(b"APRILMDL" + struct.pack("<i", 1) + struct.pack("<Q", hdr_len) + header)
+        for n in nets:
+            f.write(n)
+        f.write(params)
+
+
+def generate(path, preset="tiny", seed=1234, calibrated=True, save_npz=None):
+    d = PRESETS[preset]
+    rs = np.random.RandomState(seed + 1)
+    vocab = make_vocab(d["V"], rs)
+    W = make_weights(d, seed)
+    if calibrated:
+        W = calibrate(W, d, vocab, seed)
+    nets = [build_encoder(W, d), build_decoder(W, d), build_joiner(W, d)]
+    write_april(path, nets, params_block(d, vocab),
+                "synthetic-%s-seed%d" % (preset, seed),
+                "Synthetic random-weight lstm_transducer_stateless2 (%s dims) for parity tests" % preset)
+    if save_npz:
+        np.savez(save_npz, vocab=np.array(vocab), **W)
+    return W, vocab, d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--preset", default="tiny", choices=sorted(PRESETS))
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--npz", default=None)
+    ap.add_argument("--no-calibrate", action="store_true")
+    a = ap.parse_args()
+    generate(a.out, a.preset, a.seed, not a.no_calibrate, a.npz)
+    print("wrote", a.out, os.path.getsize(a.out), "bytes")
+
+
+if __name__ == "__main__":
+    main()
