@@ -33,6 +33,15 @@ class AprilConfig(ctypes.Structure):                     # april_api.h:164-174, 
                 ("flags", ctypes.c_int)]
 
 
+TAP = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_size_t)
+
+
+class AprilB200Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("encoder_steps", "joiner_passes", "decoder_runs", "frames", "kernel_launches",
+                                               "h2d_bytes", "d2h_bytes")] + \
+               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms")]
+
+
 REFERENCE_SYMBOLS = [
     "aam_api_init", "aam_create_model", "aam_get_name", "aam_get_description", "aam_get_language",
     "aam_get_sample_rate", "aam_free", "aas_create_session", "aas_feed_pcm16", "aas_flush",
@@ -40,7 +49,7 @@ REFERENCE_SYMBOLS = [
 ]
 B200_SYMBOLS = [
     "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_get_stats",
-    "aab_set_tap", "aab_engine_version",
+    "aab_set_tap", "aab_engine_version", "aab_debug_fbank",
 ]
 
 
@@ -73,4 +82,8 @@ class Lib:
             c.aab_device_count.argtypes, c.aab_device_count.restype = [], ctypes.c_int
             c.aab_set_device.argtypes, c.aab_set_device.restype = [ctypes.c_int], ctypes.c_int
             c.aab_engine_version.argtypes, c.aab_engine_version.restype = [], cp
+            c.aab_debug_fbank.argtypes = [vp, ctypes.POINTER(ctypes.c_short), sz, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+            c.aab_debug_fbank.restype = ctypes.c_int
+            c.aab_set_tap.argtypes, c.aab_set_tap.restype = [vp, TAP, vp], None
+            c.aab_get_stats.argtypes, c.aab_get_stats.restype = [vp, ctypes.POINTER(AprilB200Stats), ctypes.c_int], ctypes.c_int
         c.aam_api_init(1)

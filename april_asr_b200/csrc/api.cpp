@@ -1,0 +1,337 @@
+// C ABI of libaprilasr.so: the 12 entry points of april_api.h plus the additive batch API of
+// april_b200.h. Session runtime semantics follow /root/reference/src/april_session.c (sync path
+// :479-564, async path :479-493,541-545,567-585 with src/audio_provider.c's 3 s ring) — the
+// forward path itself runs in the CUDA engine (engine.cu).
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <thread>
+#include <vector>
+
+#include "../../include/april_b200.h"
+#include "engine.h"
+#include "model_loader.h"
+#include "session.h"
+
+using namespace april;
+
+// ---------------------------------------------------------------------------------------------
+// logging: same env var and levels as src/log.h:23-56, src/init.c:36-44
+// ---------------------------------------------------------------------------------------------
+enum { LEVEL_DEBUG = 0, LEVEL_INFO, LEVEL_WARNING, LEVEL_ERROR, LEVEL_NONE };
+static int g_loglevel = LEVEL_WARNING;
+static std::atomic<int> g_initialized{ 0 };
+static thread_local int tl_device = -1;
+static const char* kLevelNames[] = { "DEBUG", "INFO", "WARNING", "ERROR", "NONE" };
+#define LOG_AT(level, fmt, ...) do { if ((level) >= g_loglevel) fprintf(stderr, "libapril: (%s:%d) [%s] " fmt "\n", __FILE__, __LINE__, kLevelNames[level], ##__VA_ARGS__); } while (0)
+#define LOG_INFO(fmt, ...) LOG_AT(LEVEL_INFO, fmt, ##__VA_ARGS__)
+#define LOG_WARNING(fmt, ...) LOG_AT(LEVEL_WARNING, fmt, ##__VA_ARGS__)
+#define LOG_ERROR(fmt, ...) LOG_AT(LEVEL_ERROR, fmt, ##__VA_ARGS__)
+
+static const size_t kRingSamples = 48000;      // MAX_AUDIO, src/audio_provider.c:31
+
+struct AprilASRSession_i;
+
+struct AprilASRModel_i {
+    std::string name, description, language;
+    Params params;
+    Vocab vocab;
+    std::unique_ptr<Engine> engine;
+    // per-GPU batcher for asynchronous sessions (replaces one ProcThread per session, src/proc_thread.c)
+    std::mutex amu;
+    std::condition_variable acv;
+    std::vector<AprilASRSession_i*> async_sessions;
+    std::thread batcher;
+    bool batcher_started = false, stop = false;
+    std::mutex pass_mu;                          // held while the batcher touches sessions
+};
+
+struct AprilASRSession_i {
+    AprilASRModel_i* model = nullptr;
+    StreamFraming fr;
+    std::unique_ptr<TokenShaper> shaper;
+    AprilRecognitionResultHandler handler = nullptr;
+    void* userdata = nullptr;
+    bool sync = true;
+    bool was_flushed = false;
+    bool mismatch_reported = false;
+    // async input ring (guarded by model->amu)
+    std::vector<int16_t> ring;
+    size_t ring_count = 0;
+    bool flush_requested = false;
+};
+
+// ---------------------------------------------------------------------------------------------
+static void replay(AprilASRSession_i* s, PassItem& it, bool flush) {
+    const size_t stride = (size_t)s->model->engine->stride_ms();
+    for (int t = 0; t < it.n_steps; t++) {
+        s->shaper->begin_step(stride);
+        const int np = it.npass[(size_t)t];
+        for (int p = 0; p < np; p++) {
+            const StepDecision& d = it.decisions[(size_t)t * 3 + p];
+            bool host_blank = s->shaper->on_joiner_pass(p == 0 ? 1.0f : 0.0f, d.max_idx, d.max_val, d.blank_val);
+            if (host_blank != (d.is_blank != 0) && !s->mismatch_reported) {
+                s->mismatch_reported = true;
+                LOG_ERROR("internal: device/host greedy state diverged at step %lld pass %d", (long long)s->fr.steps_total, p);
+            }
+        }
+    }
+    if (flush) s->shaper->on_flush_end();
+}
+
+static void run_items(AprilASRModel_i* m, std::vector<AprilASRSession_i*>& ss, std::vector<PassItem>& items, bool flush) {
+    m->engine->run_pass(items);
+    for (size_t i = 0; i < ss.size(); i++) replay(ss[i], items[i], flush);
+}
+
+// ---------------------------------------------------------------------------------------------
+static void batcher_main(AprilASRModel_i* m) {
+    std::vector<AprilASRSession_i*> ss;
+    std::vector<PassItem> items;
+    std::vector<std::vector<int16_t>> chunks;
+    for (;;) {
+        ss.clear(); items.clear(); chunks.clear();
+        bool flush_pass = false;
+        {
+            std::unique_lock<std::mutex> lk(m->amu);
+            m->acv.wait(lk, [&] {
+                if (m->stop) return true;
+                for (auto* s : m->async_sessions) if (s->ring_count || s->flush_requested) return true;
+                return false;
+            });
+            if (m->stop) return;
+        }
+        std::unique_lock<std::mutex> pass_lk(m->pass_mu);     // lock order: pass_mu, then amu (aas_free does the same)
+        {
+            std::unique_lock<std::mutex> lk(m->amu);
+            // audio first; sessions whose ring is empty and that asked for a flush are flushed next
+            for (auto* s : m->async_sessions) if (s->ring_count) {
+                ss.push_back(s);
+                chunks.emplace_back(s->ring.begin(), s->ring.begin() + (long)s->ring_count);
+                s->ring_count = 0;
+            }
+            if (ss.empty()) {
+                flush_pass = true;
+                for (auto* s : m->async_sessions) if (s->flush_requested) { s->flush_requested = false; if (!s->was_flushed) { s->was_flushed = true; ss.push_back(s); } }
+            }
+        }
+        if (ss.empty()) continue;
+        items.resize(ss.size());
+        for (size_t i = 0; i < ss.size(); i++) {
+            items[i].fr = &ss[i]->fr; items[i].cookie = ss[i]; items[i].flush = flush_pass;
+            if (!flush_pass) { items[i].pcm = chunks[i].data(); items[i].count = chunks[i].size(); ss[i]->was_flushed = false; }
+        }
+        run_items(m, ss, items, flush_pass);
+    }
+}
+
+static void ensure_batcher(AprilASRModel_i* m) {
+    std::lock_guard<std::mutex> lk(m->amu);
+    if (!m->batcher_started) { m->batcher_started = true; m->batcher = std::thread(batcher_main, m); }
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+APRIL_EXPORT void aam_api_init(int version) {
+    if (version != APRIL_VERSION) LOG_WARNING("aam_api_init: client version %d, library version %d", version, APRIL_VERSION);
+    const char* env = getenv("APRIL_LOG_LEVEL");
+    if (env) for (int i = 0; i <= LEVEL_NONE; i++) if (strcmp(env, kLevelNames[i]) == 0) g_loglevel = i;
+    g_initialized = 1;
+}
+
+APRIL_EXPORT int aab_device_count(void) { return cuda_device_count_sm100(); }
+
+APRIL_EXPORT int aab_set_device(int device) {
+    if (device < 0 || device >= cuda_device_count_sm100()) return -1;
+    tl_device = device;
+    return 0;
+}
+
+APRIL_EXPORT const char* aab_engine_version(void) { return "april-b200 r1 (sm_100a; exact fp32 tier + tcgen05 tier)"; }
+
+static int pick_device() {
+    if (tl_device >= 0) return tl_device;
+    const char* e = getenv("APRIL_B200_DEVICE");
+    if (!e) e = getenv("LOCAL_RANK");
+    int n = cuda_device_count_sm100();
+    if (e && n > 0) { int v = atoi(e); if (v >= 0) return v % n; }
+    return 0;
+}
+
+APRIL_EXPORT AprilASRModel aam_create_model(const char* model_path) {
+    if (!g_initialized) { LOG_ERROR("aam: please make sure to call aam_api_init!"); return nullptr; }
+    if (!model_path) return nullptr;
+    LoadedModel lm;
+    std::string err;
+    if (!load_april_file(model_path, lm, err)) { LOG_ERROR("aam: failed to read model: %s", err.c_str()); return nullptr; }
+    std::unique_ptr<AprilASRModel_i> m(new AprilASRModel_i());
+    m->name = lm.name; m->description = lm.description; m->language = lm.language;
+    m->params = lm.params;
+    m->vocab.tokens = lm.params.tokens;
+    m->vocab.blank_id = lm.params.blank_id;
+    Engine* e = Engine::create(lm, pick_device(), err);
+    if (!e) { LOG_ERROR("aam: cannot create the B200 engine: %s", err.c_str()); return nullptr; }
+    m->engine.reset(e);
+    LOG_INFO("aam: loaded model %s on cuda:%d", m->name.c_str(), e->device());
+    return m.release();
+}
+
+APRIL_EXPORT const char* aam_get_name(AprilASRModel model) { return model->name.c_str(); }
+APRIL_EXPORT const char* aam_get_description(AprilASRModel model) { return model->description.c_str(); }
+APRIL_EXPORT const char* aam_get_language(AprilASRModel model) { return model->language.c_str(); }
+APRIL_EXPORT size_t aam_get_sample_rate(AprilASRModel model) { return (size_t)model->params.sample_rate; }
+
+APRIL_EXPORT void aam_free(AprilASRModel model) {
+    if (!model) return;
+    {
+        std::lock_guard<std::mutex> lk(model->amu);
+        model->stop = true;
+    }
+    model->acv.notify_all();
+    if (model->batcher_started) model->batcher.join();
+    delete model;
+}
+
+APRIL_EXPORT AprilASRSession aas_create_session(AprilASRModel model, AprilConfig config) {
+    if (!model) return nullptr;
+    if (config.handler == nullptr) { LOG_ERROR("No handler provided! A handler is required, please provide a handler"); return nullptr; }
+    std::unique_ptr<AprilASRSession_i> s(new AprilASRSession_i());
+    s->model = model;
+    s->sync = (config.flags & (APRIL_CONFIG_FLAG_ASYNC_RT_BIT | APRIL_CONFIG_FLAG_ASYNC_NO_RT_BIT)) == 0;
+    s->handler = config.handler;
+    s->userdata = config.userdata;
+    s->shaper.reset(new TokenShaper(&model->vocab, config.handler, config.userdata));
+    s->fr.slot = model->engine->alloc_slot();
+    if (!s->sync) {
+        s->ring.resize(kRingSamples);
+        ensure_batcher(model);
+        std::lock_guard<std::mutex> lk(model->amu);
+        model->async_sessions.push_back(s.get());
+    }
+    return s.release();
+}
+
+APRIL_EXPORT float aas_realtime_get_speedup(AprilASRSession session) { (void)session; return 1.0f; }
+
+APRIL_EXPORT void aas_free(AprilASRSession session) {
+    if (!session) return;
+    AprilASRModel_i* m = session->model;
+    if (!session->sync) {
+        std::lock_guard<std::mutex> pl(m->pass_mu);       // wait for an in-flight batcher pass
+        std::lock_guard<std::mutex> lk(m->amu);
+        auto& v = m->async_sessions;
+        for (size_t i = 0; i < v.size(); i++) if (v[i] == session) { v.erase(v.begin() + (long)i); break; }
+    }
+    m->engine->free_slot(session->fr.slot);
+    delete session;
+}
+
+APRIL_EXPORT void aas_feed_pcm16(AprilASRSession session, short* pcm16, size_t short_count) {
+    if (!session) return;
+    AprilASRModel_i* m = session->model;
+    if (session->sync) {
+        session->was_flushed = false;                                   // april_session.c:510
+        if (short_count == 0 || !pcm16) return;
+        std::vector<AprilASRSession_i*> ss{ session };
+        std::vector<PassItem> items(1);
+        items[0].fr = &session->fr; items[0].cookie = session; items[0].pcm = pcm16; items[0].count = short_count;
+        run_items(m, ss, items, false);
+        return;
+    }
+    bool ok = true;
+    {
+        std::lock_guard<std::mutex> lk(m->amu);
+        if (session->ring_count + short_count > kRingSamples) ok = false;    // ap_push_audio, src/audio_provider.c:59-64: drop the chunk
+        else { memcpy(session->ring.data() + session->ring_count, pcm16, short_count * sizeof(int16_t)); session->ring_count += short_count; }
+    }
+    m->acv.notify_one();
+    if (!ok) session->handler(session->userdata, APRIL_RESULT_ERROR_CANT_KEEP_UP, 0, nullptr);   // april_session.c:485-492
+}
+
+APRIL_EXPORT void aas_flush(AprilASRSession session) {
+    if (!session) return;
+    AprilASRModel_i* m = session->model;
+    if (session->sync) {
+        if (session->was_flushed) return;                               // april_session.c:548-550
+        session->was_flushed = true;
+        std::vector<AprilASRSession_i*> ss{ session };
+        std::vector<PassItem> items(1);
+        items[0].fr = &session->fr; items[0].cookie = session; items[0].flush = true;
+        run_items(m, ss, items, true);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(m->amu);
+        session->flush_requested = true;
+    }
+    m->acv.notify_one();
+}
+
+// ---- additive batch API (april_b200.h) -----------------------------------------------------------
+static int check_batch(AprilASRSession* sessions, size_t n) {
+    if (!sessions || n == 0) return -1;
+    std::set<AprilASRSession> seen;
+    for (size_t i = 0; i < n; i++) {
+        if (!sessions[i] || !sessions[i]->sync || sessions[i]->model != sessions[0]->model) return -1;
+        if (!seen.insert(sessions[i]).second) return -1;
+    }
+    return 0;
+}
+
+APRIL_EXPORT int aab_feed_pcm16_batch(AprilASRSession* sessions, short** pcm16, const size_t* short_count, size_t n) {
+    if (check_batch(sessions, n) != 0 || !short_count || !pcm16) return -1;
+    for (size_t i = 0; i < n; i++) if (short_count[i] && !pcm16[i]) return -1;
+    std::vector<AprilASRSession_i*> ss;
+    std::vector<PassItem> items;
+    for (size_t i = 0; i < n; i++) {
+        sessions[i]->was_flushed = false;
+        if (short_count[i] == 0) continue;
+        ss.push_back(sessions[i]);
+        PassItem it; it.fr = &sessions[i]->fr; it.cookie = sessions[i]; it.pcm = pcm16[i]; it.count = short_count[i];
+        items.push_back(std::move(it));
+    }
+    if (!ss.empty()) run_items(sessions[0]->model, ss, items, false);
+    return 0;
+}
+
+APRIL_EXPORT int aab_flush_batch(AprilASRSession* sessions, size_t n) {
+    if (check_batch(sessions, n) != 0) return -1;
+    std::vector<AprilASRSession_i*> ss;
+    std::vector<PassItem> items;
+    for (size_t i = 0; i < n; i++) {
+        if (sessions[i]->was_flushed) continue;
+        sessions[i]->was_flushed = true;
+        ss.push_back(sessions[i]);
+        PassItem it; it.fr = &sessions[i]->fr; it.cookie = sessions[i]; it.flush = true;
+        items.push_back(std::move(it));
+    }
+    if (!ss.empty()) run_items(sessions[0]->model, ss, items, true);
+    return 0;
+}
+
+APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int reset) {
+    if (!model || !out) return -1;
+    EngineStats s = model->engine->stats(reset != 0);
+    out->encoder_steps = s.encoder_steps; out->joiner_passes = s.joiner_passes; out->decoder_runs = s.decoder_runs; out->frames = s.frames;
+    out->kernel_launches = s.kernel_launches; out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
+    out->device_ms = s.device_ms; out->lstm_scan_ms = s.lstm_scan_ms; out->gemm_ms = s.gemm_ms;
+    return 0;
+}
+
+APRIL_EXPORT void aab_set_tap(AprilASRModel model, AprilB200Tap tap, void* userdata) {
+    if (!model) return;
+    model->engine->set_tap(reinterpret_cast<TapFn>(tap), userdata);
+}
+
+APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t short_count, float* out_rows, int max_rows) {
+    if (!model || !pcm16 || !out_rows) return -1;
+    return model->engine->debug_fbank(pcm16, short_count, out_rows, max_rows);
+}
+
+}  // extern "C"

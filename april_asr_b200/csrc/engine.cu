@@ -1,0 +1,563 @@
+// Engine implementation: device memory layout, pass planning (the integer logic of fbank.c's ring:
+// fbank.c:174-226,308-349) and kernel orchestration. See engine.h and DESIGN.md.
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels_simt.cuh"
+
+namespace april {
+
+#define CK(x)                                                                                              \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) {                                                                           \
+            fprintf(stderr, "libapril: (engine) [ERROR] CUDA: %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            abort();                                                                                       \
+        }                                                                                                  \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        size_t want = bytes + bytes / 4 + 4096;
+        CK(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+constexpr int CARRY_CAP = 16;       // feature rows a drained stream can still hold (< SEG after any pass)
+constexpr int FLUSH_ZEROS = 6400;   // 2 x SEGSIZE zero samples, april_session.c:500,555-556
+
+struct PassMeta {                   // per-session integers of one pass, uploaded as one block
+    int slot, carry, n_new, pad_before, n_frames, nsteps, flush_flag, keep_first, n_keep, pad0;
+    long long pcm_off;
+};
+
+struct DeviceLayer {
+    float *w_ih, *b_gate, *w_hh, *w_hr, *ff1_w, *ff1_b, *ff2_w, *ff2_b;
+    float norm_eps;
+};
+
+class EngineImpl : public Engine {
+public:
+    ModelDims d;
+    Params prm;
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    std::mutex mu;
+    EngineStats stat;
+    TapFn tap = nullptr;
+    void* tap_ud = nullptr;
+    bool profile = false;
+
+    // weights
+    std::vector<void*> owned;
+    float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *conv3_w, *conv3_b, *out_w, *out_b, *enc_proj_w, *enc_proj_b;
+    float out_norm_eps = 0.f;
+    std::vector<DeviceLayer> layers;
+    k::JoinerParams jp{};
+    k::FbankParams fp{};
+    k::ConvParams cp{};
+    float* dout_blank = nullptr;
+    int frame_N = 0, frame_shift = 0;
+
+    // per-slot state
+    int slot_cap = 0;
+    std::vector<int> free_slots;
+    float *h_store = nullptr, *c_store = nullptr, *dout_store = nullptr, *carry_store = nullptr;
+    k::GreedyState* gstate = nullptr;
+
+    // pass buffers
+    DevBuf b_pcm, b_meta, b_fb, b_xe, b_x, b_x1, b_x2, b_g, b_hout, b_f1, b_m, b_hw, b_cw, b_eo, b_rec, b_np, b_tap;
+    DevBuf b_nsteps, b_slot, b_carry, b_nnew, b_padb, b_nfr, b_flush, b_keepf, b_nkeep, b_pcmoff;
+    PinBuf p_pcm, p_meta, p_rec, p_np, p_eo, p_tap;
+
+    template <class T> T* upload(const std::vector<T>& v) {
+        T* p = nullptr;
+        CK(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+        if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        owned.push_back(p);
+        return p;
+    }
+
+    bool init(const LoadedModel& m, int device, std::string& err) {
+        dev = device;
+        d = m.w.d;
+        prm = m.params;
+        if (cudaSetDevice(dev) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10) { err = "this build targets sm_100a (B200); device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor); return false; }
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        profile = getenv("APRIL_B200_PROFILE") != nullptr;
+        if (d.D % 16 || d.H % 16 || d.F % 16 || d.J % 16 || (d.C3 * d.F3) % 16) { err = "model dims must be multiples of 16"; return false; }
+
+        const ModelWeights& w = m.w;
+        conv1_w = upload(w.conv1_w); conv1_b = upload(w.conv1_b);
+        conv2_w = upload(w.conv2_w); conv2_b = upload(w.conv2_b);
+        conv3_w = upload(w.conv3_w); conv3_b = upload(w.conv3_b);
+        out_w = upload(w.out_w); out_b = upload(w.out_b); out_norm_eps = w.out_norm_eps;
+        for (auto& lw : w.layers) {
+            DeviceLayer dl{};
+            std::vector<float> bsum(lw.b_ih.size());
+            for (size_t i = 0; i < bsum.size(); i++) bsum[i] = lw.b_ih[i] + lw.b_hh[i];
+            dl.w_ih = upload(lw.w_ih); dl.b_gate = upload(bsum); dl.w_hh = upload(lw.w_hh); dl.w_hr = upload(lw.w_hr);
+            dl.ff1_w = upload(lw.ff1_w); dl.ff1_b = upload(lw.ff1_b); dl.ff2_w = upload(lw.ff2_w); dl.ff2_b = upload(lw.ff2_b);
+            dl.norm_eps = lw.norm_eps;
+            layers.push_back(dl);
+        }
+        enc_proj_w = upload(w.enc_proj_w); enc_proj_b = upload(w.enc_proj_b);
+
+        // vocabulary flags (april_session.c:338-351)
+        std::vector<uint8_t> vf((size_t)d.V, 0);
+        for (int i = 0; i < d.V; i++) {
+            const std::string& t = prm.tokens[(size_t)i];
+            uint8_t f = 0;
+            if (!t.empty() && t[0] == ' ') f |= k::VF_SPACE;
+            if (t.size() == 1 && (t[0] == '.' || t[0] == '!' || t[0] == '?')) f |= k::VF_EOS;
+            if (t.size() == 1 && t[0] == ',') f |= k::VF_COMMA;
+            if (!t.empty() && t[0] >= '0' && t[0] <= '9') f |= k::VF_DIGIT;
+            if (t.size() == 1 && t[0] == '.') f |= k::VF_DOT;
+            vf[(size_t)i] = f;
+        }
+        jp.J = d.J; jp.E = d.E; jp.V = d.V; jp.blank = prm.blank_id;
+        jp.emb = upload(w.emb); jp.dec_conv = upload(w.dec_conv_w); jp.dec_w = upload(w.dec_proj_w); jp.dec_b = upload(w.dec_proj_b);
+        jp.join_w = upload(w.join_w); jp.join_b = upload(w.join_b); jp.vflags = upload(vf);
+
+        // front-end tables: generate_povey_window fbank.c:49-55, generate_banks fbank.c:65-95
+        int window_size = prm.frame_length_ms * prm.sample_rate / 1000;
+        frame_shift = prm.frame_shift_ms * prm.sample_rate / 1000;
+        int N = window_size;
+        if (prm.round_pow2) { N -= 1; N |= N >> 1; N |= N >> 2; N |= N >> 4; N |= N >> 8; N |= N >> 16; N += 1; }
+        if ((N & (N - 1)) != 0 || N < 64 || N > 1024) { err = "front-end: padded window must be a power of two in [64, 1024]"; return false; }
+        frame_N = N;
+        std::vector<float> win((size_t)N);
+        for (int i = 0; i < N; i++) win[(size_t)i] = (float)pow(0.5 - 0.5 * cos((double)i / (double)N * 6.283185307), 0.85);
+        std::vector<double2> tw((size_t)N / 2);
+        for (int i = 0; i < N / 2; i++) { double a = 2.0 * M_PI * (double)i / (double)N; tw[(size_t)i] = make_double2(cos(a), -sin(a)); }
+        int nb = N / 2, mel = prm.mel_features;
+        std::vector<float> bank((size_t)mel * nb, 0.f);
+        {
+            int high = prm.mel_high == 0 ? prm.sample_rate / 2 : prm.mel_high;
+            auto mel_scale = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };
+            volatile float bw = (float)prm.sample_rate / (float)N;
+            volatile float mel_low = (float)mel_scale((double)prm.mel_low), mel_high = (float)mel_scale((double)high);
+            volatile float delta = (mel_high - mel_low) / ((float)mel + 1.0f);
+            for (int i = 0; i < mel; i++) {
+                volatile float left = mel_low + (float)i * delta;
+                volatile float center = left + delta;
+                volatile float right = center + delta;
+                for (int j = 0; j < nb; j++) {
+                    volatile float freq = bw * (float)j;
+                    volatile float mf = (float)mel_scale((double)freq);
+                    float wgt = 0.f;
+                    if (mf > left && mf < right) {
+                        if (mf <= center) { volatile float a = mf - left, c = center - left; wgt = a / c; }
+                        else { volatile float a = right - mf, c = right - center; wgt = a / c; }
+                    }
+                    bank[(size_t)i * nb + j] = wgt;
+                }
+            }
+        }
+        std::vector<int> ms((size_t)mel, 0), mc((size_t)mel, 0), mo((size_t)mel, 0);
+        std::vector<float> mw;
+        for (int i = 0; i < mel; i++) {
+            int lo = -1, hi = -1;
+            for (int j = 0; j < nb; j++) if (bank[(size_t)i * nb + j] != 0.f) { if (lo < 0) lo = j; hi = j; }
+            mo[(size_t)i] = (int)mw.size();
+            if (lo >= 0) { ms[(size_t)i] = lo; mc[(size_t)i] = hi - lo + 1; for (int j = lo; j <= hi; j++) mw.push_back(bank[(size_t)i * nb + j]); }
+        }
+        fp.N = N; fp.log2N = 0; while ((1 << fp.log2N) < N) fp.log2N++;
+        fp.shift = frame_shift; fp.mel = mel; fp.nbins = nb;
+        fp.pad_value = (float)log((double)1.1920928955078125e-07f);
+        fp.window = upload(win); fp.twiddle = upload(tw); fp.mel_start = upload(ms); fp.mel_count = upload(mc); fp.mel_off = upload(mo); fp.mel_w = upload(mw);
+        CK(cudaFuncSetAttribute(k::fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * N * (int)sizeof(double)));
+
+        cp.SEG = d.SEG; cp.MEL = d.MEL; cp.STEP = d.STEP; cp.C1 = d.C1; cp.C2 = d.C2; cp.C3 = d.C3;
+        cp.T1 = d.SEG - 2; cp.F1 = d.MEL - 2; cp.T2 = (cp.T1 - 3) / 2 + 1; cp.F2 = (cp.F1 - 3) / 2 + 1; cp.F3 = d.F3;
+        cp.w1 = conv1_w; cp.b1 = conv1_b; cp.w2 = conv2_w; cp.b2 = conv2_b; cp.w3 = conv3_w; cp.b3 = conv3_b;
+        CK(cudaFuncSetAttribute(k::conv_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem()));
+
+        CK(cudaMalloc(&dout_blank, sizeof(float) * (size_t)d.J));
+        k::decoder_kernel<<<1, 256, (size_t)(d.E + d.J) * sizeof(float), st>>>(jp, prm.blank_id, prm.blank_id, dout_blank);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        grow_slots(64);
+        return true;
+    }
+
+    size_t conv_smem() const {
+        return sizeof(float) * ((size_t)cp.SEG * cp.MEL + (size_t)cp.C1 * cp.T1 * cp.F1 + (size_t)cp.C2 * cp.T2 * cp.F2 + (size_t)cp.C2 * cp.C1 * 9);
+    }
+
+    ~EngineImpl() override {
+        cudaSetDevice(dev);
+        if (st) cudaStreamSynchronize(st);
+        for (void* p : owned) cudaFree(p);
+        cudaFree(dout_blank); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
+        if (st) cudaStreamDestroy(st);
+    }
+
+    template <class T> void regrow(T*& p, size_t old_n, size_t new_n) {
+        T* q = nullptr;
+        CK(cudaMalloc(&q, new_n * sizeof(T)));
+        CK(cudaMemsetAsync(q, 0, new_n * sizeof(T), st));
+        if (p && old_n) CK(cudaMemcpyAsync(q, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        if (p) CK(cudaFree(p));
+        p = q;
+    }
+
+    void grow_slots(int new_cap) {
+        size_t o = (size_t)slot_cap, n = (size_t)new_cap;
+        regrow(h_store, o * d.L * d.D, n * d.L * d.D);
+        regrow(c_store, o * d.L * d.H, n * d.L * d.H);
+        regrow(dout_store, o * d.J, n * d.J);
+        regrow(carry_store, o * CARRY_CAP * d.MEL, n * CARRY_CAP * d.MEL);
+        regrow(gstate, o, n);
+        for (int i = new_cap - 1; i >= slot_cap; i--) free_slots.push_back(i);
+        slot_cap = new_cap;
+    }
+
+    int alloc_slot() override {
+        std::lock_guard<std::mutex> lk(mu);
+        CK(cudaSetDevice(dev));
+        if (free_slots.empty()) grow_slots(slot_cap * 2);
+        int s = free_slots.back();
+        free_slots.pop_back();
+        // zero h/c (calloc'ed tensors, ort_util.h:48-50), context = blanks + decoder output (april_session.c:432-438)
+        CK(cudaMemsetAsync(h_store + (size_t)s * d.L * d.D, 0, sizeof(float) * (size_t)d.L * d.D, st));
+        CK(cudaMemsetAsync(c_store + (size_t)s * d.L * d.H, 0, sizeof(float) * (size_t)d.L * d.H, st));
+        k::GreedyState g{};
+        g.ctx0 = g.ctx1 = prm.blank_id;
+        CK(cudaMemcpyAsync(gstate + s, &g, sizeof g, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dout_store + (size_t)s * d.J, dout_blank, sizeof(float) * (size_t)d.J, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        return s;
+    }
+
+    void free_slot(int slot) override {
+        std::lock_guard<std::mutex> lk(mu);
+        if (slot >= 0) free_slots.push_back(slot);
+    }
+
+    EngineStats stats(bool reset) override {
+        std::lock_guard<std::mutex> lk(mu);
+        EngineStats s = stat;
+        if (reset) stat = EngineStats();
+        return s;
+    }
+    void set_tap(TapFn fn, void* ud) override { std::lock_guard<std::mutex> lk(mu); tap = fn; tap_ud = ud; }
+    int stride_ms() const override { return prm.segment_step * prm.frame_shift_ms; }   // fbank.c:359-361
+    int device() const override { return dev; }
+
+    int debug_fbank(const int16_t* pcm, size_t n, float* out_rows, int max_rows) override {
+        std::lock_guard<std::mutex> lk(mu);
+        CK(cudaSetDevice(dev));
+        int nf = n >= (size_t)frame_N ? (int)((n - (size_t)frame_N) / (size_t)frame_shift) + 1 : 0;
+        nf = std::min(nf, max_rows);
+        if (nf <= 0) return 0;
+        b_pcm.ensure(n * sizeof(int16_t));
+        CK(cudaMemcpyAsync(b_pcm.p, pcm, n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        int hm[4] = { 0, nf, nf, 0 };                     // pad_before, n_frames, n_new, carry
+        long long off = 0;
+        b_meta.ensure(64);
+        CK(cudaMemcpyAsync(b_meta.p, hm, sizeof hm, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync((char*)b_meta.p + 32, &off, sizeof off, cudaMemcpyHostToDevice, st));
+        b_fb.ensure(sizeof(float) * (size_t)nf * d.MEL);
+        int* dm = b_meta.as<int>();
+        k::fbank_kernel<<<dim3((unsigned)((nf + 3) / 4), 1), 128, (size_t)4 * 3 * frame_N * sizeof(double), st>>>(
+            fp, b_pcm.as<int16_t>(), reinterpret_cast<long long*>((char*)b_meta.p + 32), dm, dm + 1, dm + 2, dm + 3, b_fb.as<float>(), nf);
+        launch_check();
+        CK(cudaMemcpyAsync(out_rows, b_fb.p, sizeof(float) * (size_t)nf * d.MEL, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return nf;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void launch_check() { stat.kernel_launches++; CK(cudaGetLastError()); }
+
+    void gemm(int epi, const float* A, const float* W, const float* bias, const float* R, float* C, int M, int N, int K) {
+        dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+        if (epi == k::EPI_BIAS) k::gemm_simt_kernel<k::EPI_BIAS><<<grid, 256, 0, st>>>(A, W, bias, R, C, M, N, K);
+        else if (epi == k::EPI_BIAS_DSWISH) k::gemm_simt_kernel<k::EPI_BIAS_DSWISH><<<grid, 256, 0, st>>>(A, W, bias, R, C, M, N, K);
+        else k::gemm_simt_kernel<k::EPI_BIAS_RESIDUAL><<<grid, 256, 0, st>>>(A, W, bias, R, C, M, N, K);
+        launch_check();
+    }
+
+    double sync_ms_since(std::chrono::steady_clock::time_point& t0) {
+        CK(cudaStreamSynchronize(st));
+        auto t1 = std::chrono::steady_clock::now();
+        double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        return ms;
+    }
+
+    void run_pass(std::vector<PassItem>& items) override {
+        std::lock_guard<std::mutex> lk(mu);
+        const int B = (int)items.size();
+        if (B == 0) return;
+        CK(cudaSetDevice(dev));
+        const int SEG = d.SEG, STEP = d.STEP, N = frame_N, shift = frame_shift, MEL = d.MEL;
+
+        // ---- plan (integer logic of fbank.c's ring + april_session.c:547-559) ---------------------
+        std::vector<PassMeta> meta((size_t)B);
+        size_t pcm_total = 0;
+        int max_new = 0, max_rows = 0, Tmax = 0;
+        for (int b = 0; b < B; b++) {
+            PassItem& it = items[(size_t)b];
+            StreamFraming& fr = *it.fr;
+            PassMeta& m = meta[(size_t)b];
+            m = PassMeta{};
+            m.slot = fr.slot;
+            m.carry = (int)fr.avail;
+            long long avail = fr.avail, avail_f = fr.avail_f;
+            int steps = 0, pad_before = 0, pad_after = 0;
+            auto drain = [&]() { while (avail >= SEG) { steps++; avail -= STEP; avail_f -= STEP; } };
+            auto flush_loop = [&](int& pads) {                                   // while(fbank_flush) aas_infer
+                while (avail_f >= -(long long)(SEG * 3)) { while (avail < SEG) { pads++; avail++; } drain(); }
+            };
+            size_t n_in = it.flush ? (size_t)FLUSH_ZEROS : it.count;
+            if (it.flush) flush_loop(pad_before);
+            size_t n_buf = fr.tail.size() + n_in;
+            int nf = n_buf >= (size_t)N ? (int)((n_buf - (size_t)N) / (size_t)shift) + 1 : 0;
+            avail += nf;
+            if (nf > 0) avail_f = avail;                                          // fbank.c:299-300
+            if (it.flush) flush_loop(pad_after); else drain();
+            m.pad_before = pad_before; m.n_frames = nf; m.n_new = pad_before + nf + pad_after;
+            m.nsteps = steps; m.flush_flag = it.flush ? 1 : 0;
+            m.keep_first = steps * STEP; m.n_keep = m.carry + m.n_new - steps * STEP;
+            if (m.n_keep != (int)avail || m.n_keep > CARRY_CAP || m.n_keep < 0) { fprintf(stderr, "libapril: (engine) [ERROR] internal: carry accounting\n"); abort(); }
+            m.pcm_off = (long long)pcm_total;
+            pcm_total += (n_buf + 7) & ~(size_t)7;
+            max_new = std::max(max_new, m.n_new);
+            max_rows = std::max(max_rows, m.carry + m.n_new);
+            Tmax = std::max(Tmax, steps);
+            fr.avail = avail; fr.avail_f = avail_f; fr.steps_total += steps;
+            it.n_steps = steps;
+            stat.frames += (uint64_t)nf;
+            stat.encoder_steps += (uint64_t)steps;
+        }
+        const int row_pitch = std::max(max_rows, 1);
+
+        // ---- stage PCM: [tail | new samples or zeros] per session ---------------------------------
+        p_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
+        int16_t* hp = p_pcm.as<int16_t>();
+        for (int b = 0; b < B; b++) {
+            PassItem& it = items[(size_t)b];
+            StreamFraming& fr = *it.fr;
+            int16_t* dst = hp + meta[(size_t)b].pcm_off;
+            size_t nt = fr.tail.size(), n_in = it.flush ? (size_t)FLUSH_ZEROS : it.count;
+            if (nt) memcpy(dst, fr.tail.data(), nt * sizeof(int16_t));
+            if (it.flush) memset(dst + nt, 0, n_in * sizeof(int16_t));
+            else if (n_in) memcpy(dst + nt, it.pcm, n_in * sizeof(int16_t));
+            size_t n_buf = nt + n_in;
+            size_t consumed = (size_t)meta[(size_t)b].n_frames * (size_t)shift;   // next frame starts here (fbank.c:198-224)
+            if (consumed > n_buf) consumed = n_buf;
+            fr.tail.assign(dst + consumed, dst + n_buf);
+        }
+        auto t_host = std::chrono::steady_clock::now();
+        cudaEvent_t ev0, ev1;
+        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+        CK(cudaEventRecord(ev0, st));
+        b_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
+        if (pcm_total) CK(cudaMemcpyAsync(b_pcm.p, hp, pcm_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        stat.h2d_bytes += pcm_total * sizeof(int16_t);
+
+        // per-session ints as struct-of-arrays
+        const size_t nI = (size_t)B;
+        const size_t meta_bytes = (9 * nI + (nI & 1)) * sizeof(int) + nI * sizeof(long long);
+        p_meta.ensure(meta_bytes);
+        int* hm = p_meta.as<int>();
+        int *h_slot = hm, *h_carry = hm + nI, *h_nnew = hm + 2 * nI, *h_padb = hm + 3 * nI, *h_nfr = hm + 4 * nI, *h_nsteps = hm + 5 * nI,
+            *h_flush = hm + 6 * nI, *h_keepf = hm + 7 * nI, *h_nkeep = hm + 8 * nI;
+        long long* h_off = reinterpret_cast<long long*>(hm + 9 * nI + (nI & 1));
+        for (int b = 0; b < B; b++) {
+            const PassMeta& m = meta[(size_t)b];
+            h_slot[b] = m.slot; h_carry[b] = m.carry; h_nnew[b] = m.n_new; h_padb[b] = m.pad_before; h_nfr[b] = m.n_frames; h_nsteps[b] = m.nsteps;
+            h_flush[b] = m.flush_flag; h_keepf[b] = m.keep_first; h_nkeep[b] = m.n_keep; h_off[b] = m.pcm_off;
+        }
+        b_meta.ensure(meta_bytes);
+        CK(cudaMemcpyAsync(b_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+        stat.h2d_bytes += meta_bytes;
+        int* dm = b_meta.as<int>();
+        int *d_slot = dm, *d_carry = dm + nI, *d_nnew = dm + 2 * nI, *d_padb = dm + 3 * nI, *d_nfr = dm + 4 * nI, *d_nsteps = dm + 5 * nI,
+            *d_flush = dm + 6 * nI, *d_keepf = dm + 7 * nI, *d_nkeep = dm + 8 * nI;
+        long long* d_off = reinterpret_cast<long long*>(dm + 9 * nI + (nI & 1));
+
+        // ---- front-end ------------------------------------------------------------------------------
+        b_fb.ensure(sizeof(float) * (size_t)B * row_pitch * MEL);
+        float* FB = b_fb.as<float>();
+        k::carry_in_kernel<<<B, 128, 0, st>>>(carry_store, d_slot, d_carry, FB, row_pitch, MEL, CARRY_CAP); launch_check();
+        if (max_new > 0) {
+            dim3 grid((unsigned)((max_new + 3) / 4), (unsigned)B);
+            k::fbank_kernel<<<grid, 128, (size_t)4 * 3 * N * sizeof(double), st>>>(fp, b_pcm.as<int16_t>(), d_off, d_padb, d_nfr, d_nnew, d_carry, FB, row_pitch);
+            launch_check();
+        }
+        double ms_front = profile ? sync_ms_since(t_host) : 0;
+
+        // ---- encoder + search, in time chunks -------------------------------------------------------
+        size_t rec_bytes = 0, np_bytes = 0;
+        const bool want_tap = tap != nullptr;
+        if (Tmax > 0) {
+            const size_t row_budget = 160 * 1024;                                  // rows per chunk (bounds the activations to a few GB)
+            int Tc = (int)std::max<size_t>(1, std::min<size_t>((size_t)Tmax, row_budget / (size_t)B));
+            const size_t Mc = (size_t)Tc * B;
+            const int L = d.L, D = d.D, H = d.H, F = d.F, J = d.J, KE = d.C3 * d.F3;
+            b_xe.ensure(sizeof(float) * Mc * KE); b_x.ensure(sizeof(float) * Mc * D); b_x1.ensure(sizeof(float) * Mc * D); b_x2.ensure(sizeof(float) * Mc * D);
+            b_g.ensure(sizeof(float) * Mc * 4 * H); b_hout.ensure(sizeof(float) * Mc * D); b_f1.ensure(sizeof(float) * Mc * F);
+            b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
+            b_eo.ensure(sizeof(float) * Mc * J);
+            rec_bytes = sizeof(k::DecisionRecord) * (size_t)B * Tmax * 3; np_bytes = sizeof(int) * (size_t)B * Tmax;
+            b_rec.ensure(rec_bytes); b_np.ensure(np_bytes);
+            if (want_tap) { b_tap.ensure(sizeof(float) * (size_t)B * Tmax * 3 * d.V); p_tap.ensure(sizeof(float) * (size_t)B * Tmax * 3 * d.V); p_eo.ensure(sizeof(float) * (size_t)Tmax * B * J); }
+            float *Xe = b_xe.as<float>(), *X = b_x.as<float>(), *X1 = b_x1.as<float>(), *X2 = b_x2.as<float>(), *G = b_g.as<float>(), *Hout = b_hout.as<float>(),
+                  *F1 = b_f1.as<float>(), *Ms = b_m.as<float>(), *Hw = b_hw.as<float>(), *Cw = b_cw.as<float>(), *EO = b_eo.as<float>();
+            k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
+            k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
+            const size_t greedy_smem = sizeof(float) * (size_t)(3 * J + d.E);
+            for (int t0 = 0; t0 < Tmax; t0 += Tc) {
+                const int tc = std::min(Tc, Tmax - t0);
+                const int M = tc * B;
+                k::conv_embed_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(cp, FB, row_pitch, d_nsteps, t0, B, Xe); launch_check();
+                gemm(k::EPI_BIAS, Xe, out_w, out_b, nullptr, X1, M, D, KE);
+                k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, M, D, out_norm_eps); launch_check();
+                for (int l = 0; l < L; l++) {
+                    const DeviceLayer& w = layers[(size_t)l];
+                    auto tg = std::chrono::steady_clock::now();
+                    if (profile) CK(cudaStreamSynchronize(st));
+                    gemm(k::EPI_BIAS, X, w.w_ih, w.b_gate, nullptr, G, M, 4 * H, D);
+                    if (profile) stat.gemm_ms += sync_ms_since(tg);
+                    float* hw = Hw + (size_t)l * B * D;
+                    float* cw = Cw + (size_t)l * B * H;
+                    for (int t = 0; t < tc; t++) {
+                        k::lstm_gates_kernel<<<dim3((unsigned)(H / 16), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
+                            G + (size_t)t * B * 4 * H, hw, w.w_hh, cw, Ms, d_nsteps, t0 + t, B, D, H);
+                        launch_check();
+                        k::lstm_proj_kernel<<<dim3((unsigned)((D + 63) / 64), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
+                            Ms, w.w_hr, hw, Hout + (size_t)t * B * D, d_nsteps, t0 + t, B, D, H);
+                        launch_check();
+                    }
+                    if (profile) stat.lstm_scan_ms += sync_ms_since(tg);
+                    k::add_rows_kernel<<<(unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, 148 * 8), 256, 0, st>>>(
+                        reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Hout), reinterpret_cast<float4*>(X1), (size_t)M * D / 4);
+                    launch_check();
+                    gemm(k::EPI_BIAS_DSWISH, X1, w.ff1_w, w.ff1_b, nullptr, F1, M, F, D);
+                    gemm(k::EPI_BIAS_RESIDUAL, F1, w.ff2_w, w.ff2_b, X1, X2, M, D, F);
+                    if (profile) stat.gemm_ms += sync_ms_since(tg);
+                    k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
+                }
+                gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
+                const int last = (t0 + tc >= Tmax) ? 1 : 0;
+                k::greedy_kernel<<<B, 256, greedy_smem, st>>>(jp, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate, dout_store, dout_blank,
+                                                             b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc);
+                launch_check();
+                if (want_tap) { CK(cudaMemcpyAsync(p_eo.as<float>() + (size_t)t0 * B * J, EO, sizeof(float) * (size_t)M * J, cudaMemcpyDeviceToHost, st)); stat.d2h_bytes += sizeof(float) * (size_t)M * J; }
+            }
+            k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
+            k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
+            p_rec.ensure(rec_bytes); p_np.ensure(np_bytes);
+            CK(cudaMemcpyAsync(p_rec.p, b_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(p_np.p, b_np.p, np_bytes, cudaMemcpyDeviceToHost, st));
+            stat.d2h_bytes += rec_bytes + np_bytes;
+            if (want_tap) { CK(cudaMemcpyAsync(p_tap.p, b_tap.p, sizeof(float) * (size_t)B * Tmax * 3 * d.V, cudaMemcpyDeviceToHost, st)); }
+        } else {
+            // no encoder step, but a flush must still clear the context on the device (april_session.c:561-563)
+            bool any_flush = false;
+            for (int b = 0; b < B; b++) any_flush |= items[(size_t)b].flush;
+            if (any_flush) {
+                b_rec.ensure(sizeof(k::DecisionRecord) * 3); b_np.ensure(sizeof(int));
+                b_eo.ensure(sizeof(float) * (size_t)d.J);
+                k::greedy_kernel<<<B, 256, sizeof(float) * (size_t)(3 * d.J + d.E), st>>>(jp, b_eo.as<float>(), d_nsteps, d_slot, d_flush, B, 1, 0, stride_ms(), gstate, dout_store,
+                                                                                         dout_blank, b_rec.as<k::DecisionRecord>(), b_np.as<int>(), nullptr, 1, 1);
+                launch_check();
+            }
+        }
+        k::carry_out_kernel<<<B, 128, 0, st>>>(carry_store, d_slot, d_keepf, d_nkeep, FB, row_pitch, MEL, CARRY_CAP); launch_check();
+        CK(cudaEventRecord(ev1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        stat.device_ms += ms;
+        CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
+        (void)ms_front;
+
+        // ---- hand decisions back ----------------------------------------------------------------------
+        const k::DecisionRecord* hr = p_rec.as<k::DecisionRecord>();
+        const int* hn = p_np.as<int>();
+        for (int b = 0; b < B; b++) {
+            PassItem& it = items[(size_t)b];
+            it.npass.assign((size_t)it.n_steps, 0);
+            it.decisions.assign((size_t)it.n_steps * 3, StepDecision{});
+            for (int t = 0; t < it.n_steps; t++) {
+                int np = hn[(size_t)b * Tmax + t];
+                it.npass[(size_t)t] = np;
+                stat.joiner_passes += (uint64_t)np;
+                for (int p = 0; p < np; p++) {
+                    const k::DecisionRecord& r = hr[((size_t)b * Tmax + t) * 3 + p];
+                    it.decisions[(size_t)t * 3 + p] = StepDecision{ r.max_idx, r.is_blank, r.max_val, r.blank_val };
+                    if (!r.is_blank) stat.decoder_runs++;
+                }
+            }
+        }
+        if (want_tap && Tmax > 0) {
+            const float* eo = p_eo.as<float>();
+            const float* lg = p_tap.as<float>();
+            for (int b = 0; b < B; b++) {
+                PassItem& it = items[(size_t)b];
+                for (int t = 0; t < it.n_steps; t++) {
+                    tap(tap_ud, it.cookie, 0, eo + ((size_t)t * B + b) * d.J, (size_t)d.J);
+                    for (int p = 0; p < it.npass[(size_t)t]; p++) tap(tap_ud, it.cookie, 2, lg + (((size_t)b * Tmax + t) * 3 + p) * d.V, (size_t)d.V);
+                }
+            }
+        }
+    }
+};
+
+}  // namespace
+
+Engine* Engine::create(const LoadedModel& m, int device, std::string& err) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { err = "no CUDA device available (this library has no CPU fallback)"; return nullptr; }
+    if (device < 0 || device >= n) { err = "CUDA device index out of range"; return nullptr; }
+    EngineImpl* e = new EngineImpl();
+    if (!e->init(m, device, err)) { delete e; return nullptr; }
+    return e;
+}
+
+int cuda_device_count_sm100() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int i = 0; i < n; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++; }
+    return ok;
+}
+
+}  // namespace april

@@ -1,0 +1,69 @@
+// Device engine: owns the weights of one model on one B200 and runs batched passes of the hot path
+// (fbank -> encoder -> decoder/joiner -> greedy decisions) over many sessions.
+// Replaces the three g_ort->Run call sites (april_session.c:145,160,176), the tensor allocation
+// (april_session.c:40-58) and the fbank_* calls (april_session.c:35,441-442,528,552-559).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "model_loader.h"
+
+namespace april {
+
+struct StepDecision {           // mirrors k::DecisionRecord
+    int32_t max_idx;
+    int32_t is_blank;
+    float max_val;
+    float blank_val;
+};
+
+// Host-side framing state of one stream (what OnlineFBank_i keeps: fbank.c:98-127), minus the data
+// that lives on the device.
+struct StreamFraming {
+    int slot = -1;
+    std::vector<int16_t> tail;      // samples from the start of the next frame onwards (prev_leftover)
+    long long avail = 0;            // temp_segment_avail
+    long long avail_f = 0;          // temp_segment_avail_f
+    long long steps_total = 0;
+};
+
+struct PassItem {
+    StreamFraming* fr = nullptr;
+    void* cookie = nullptr;         // handed back to the tap
+    const int16_t* pcm = nullptr;
+    size_t count = 0;
+    bool flush = false;
+    // outputs of the pass:
+    int n_steps = 0;
+    std::vector<int> npass;                 // [n_steps]
+    std::vector<StepDecision> decisions;    // [n_steps][3]
+};
+
+struct EngineStats {
+    uint64_t encoder_steps = 0, joiner_passes = 0, decoder_runs = 0, frames = 0, kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    double device_ms = 0, lstm_scan_ms = 0, gemm_ms = 0;
+};
+
+typedef void (*TapFn)(void* userdata, void* cookie, int net, const float* data, size_t n);
+
+class Engine {
+public:
+    static Engine* create(const LoadedModel& m, int device, std::string& err);
+    virtual ~Engine() {}
+    virtual int alloc_slot() = 0;           // device-side per-stream state (h, c, context, carry rows); zeros / blanks
+    virtual void free_slot(int slot) = 0;
+    virtual void run_pass(std::vector<PassItem>& items) = 0;   // aborts on CUDA errors (ORT_ABORT_ON_ERROR convention)
+    virtual EngineStats stats(bool reset) = 0;
+    virtual void set_tap(TapFn fn, void* userdata) = 0;
+    // test hook: log-mel rows of one standalone stream (frames [160 i, 160 i + N)), returns the row count
+    virtual int debug_fbank(const int16_t* pcm, size_t n, float* out_rows, int max_rows) = 0;
+    virtual int stride_ms() const = 0;
+    virtual int device() const = 0;
+};
+
+int cuda_device_count_sm100();
+
+}  // namespace april

@@ -1,0 +1,74 @@
+/*
+ * april_b200.h — additive C ABI of the B200 engine (not part of the reference's april_api.h).
+ *
+ * The reference processes one session per call (src/april_session.c:479-564, batch hard-wired to
+ * 1: src/params.c:71, src/april_session.c:51-55). The GPU engine batches the per-frame hot loop
+ * (fbank -> encoder -> decoder/joiner -> greedy search) over many sessions; these entry points
+ * expose that batching for SYNCHRONOUS sessions without changing any reference type: the session
+ * handles, AprilConfig, the handler and its calling convention are exactly april_api.h's.
+ * Semantics: identical to calling aas_feed_pcm16 / aas_flush on each session in index order —
+ * every session's handler runs on the caller's thread before the call returns, session i's
+ * callbacks complete before session i+1's start — but all sessions advance through ONE batched
+ * device pass. Plain pointers and sizes only.
+ *
+ * Reference-side binding a maintainer would add: see INTEGRATION.md.
+ */
+#ifndef APRIL_B200_H
+#define APRIL_B200_H
+
+#include "april_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Batched aas_feed_pcm16 (replaces N calls of src/april_session.c:479). All sessions must be
+ * synchronous sessions of the same model. pcm16[i] may be NULL iff short_count[i] == 0.
+ * Returns 0, or -1 on invalid arguments (nothing processed). Device errors abort(), as ORT errors do
+ * in the reference (src/ort_util.h:29-38). */
+APRIL_EXPORT int aab_feed_pcm16_batch(AprilASRSession* sessions, short** pcm16,
+                                      const size_t* short_count, size_t n_sessions);
+
+/* Batched aas_flush (replaces N calls of src/april_session.c:541). */
+APRIL_EXPORT int aab_flush_batch(AprilASRSession* sessions, size_t n_sessions);
+
+/* Number of usable sm_100 devices; 0 means the library cannot run (there is no CPU fallback). */
+APRIL_EXPORT int aab_device_count(void);
+
+/* Select the CUDA device used by models created afterwards on this thread's behalf (default: env
+ * APRIL_B200_DEVICE, else LOCAL_RANK, else 0). Sessions inherit their model's device. */
+APRIL_EXPORT int aab_set_device(int device);
+
+typedef struct AprilB200Stats {
+    uint64_t encoder_steps;     /* session-steps run through the encoder */
+    uint64_t joiner_passes;     /* joiner evaluations (1..3 per session-step) */
+    uint64_t decoder_runs;      /* decoder evaluations on device */
+    uint64_t frames;            /* fbank frames computed */
+    uint64_t kernel_launches;   /* CUDA kernels launched by the engine */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    double   device_ms;         /* CUDA-event time of all engine passes */
+    double   lstm_scan_ms;      /* ... of which the recurrent scan kernels */
+    double   gemm_ms;           /* ... of which the time-batched GEMMs */
+} AprilB200Stats;
+
+/* Cumulative statistics of a model's engine; reset != 0 zeroes them after reading. */
+APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int reset);
+
+/* Debug/parity tap: after every engine pass, called once per session-step with the encoder output
+ * (net = 0, n = joiner dim) and once per joiner pass with the raw logits (net = 2, n = vocab) —
+ * the same quantities the oracle's fake_ort_set_tap reports for the reference's OrtRun calls
+ * (src/april_session.c:145,176). Costs extra device->host traffic; NULL disables. */
+typedef void (*AprilB200Tap)(void* userdata, AprilASRSession session, int net, const float* data, size_t n);
+APRIL_EXPORT void aab_set_tap(AprilASRModel model, AprilB200Tap tap, void* userdata);
+
+/* Test hook: run only the front-end kernel (F1/F2, src/fbank.c:174-306) on one standalone stream and
+ * return its log-mel rows ([rows][mel_features] floats). Returns the number of rows written. */
+APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t short_count, float* out_rows, int max_rows);
+
+APRIL_EXPORT const char* aab_engine_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

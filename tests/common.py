@@ -1,0 +1,145 @@
+"""Shared helpers for the parity tests. The ORACLE (oracle/_ref/libaprilasr_ref.so = the reference's
+own host sources + a CPU fp32 restatement of its ONNX graphs) is only ever used here as the checker."""
+import ctypes
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import april_asr_b200 as A  # noqa: E402
+from april_asr_b200 import _ffi  # noqa: E402
+from gen_pcm import gen_stream  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BUILD = os.path.join(ROOT, "build")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "libaprilasr_ref.so")
+PRODUCT_SO = os.path.join(ROOT, "april_asr_b200", "lib", "libaprilasr.so")
+TINY_MODEL = os.path.join(GOLDEN, "tiny.april")
+
+
+def model_path(preset):
+    if preset == "tiny":
+        return TINY_MODEL
+    os.makedirs(BUILD, exist_ok=True)
+    p = os.path.join(BUILD, preset + ".april")
+    if not os.path.exists(p):
+        import make_synthetic_april
+        make_synthetic_april.generate(p, preset, 1234)
+    return p
+
+
+_libs = {}
+
+
+def oracle_lib():
+    if "o" not in _libs:
+        if not os.path.exists(ORACLE_SO):
+            return None
+        lib = A.Lib(ORACLE_SO)
+        lib.c.fake_ort_set_tap.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.c.fake_ort_get_run_counts.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+        _libs["o"] = lib
+    return _libs["o"]
+
+
+def product_lib():
+    if "p" not in _libs:
+        _libs["p"] = A.Lib(PRODUCT_SO)
+    return _libs["p"]
+
+
+ORACLE_TAP = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_size_t)
+
+
+class Collected:
+    def __init__(self):
+        self.log = []          # (result_type, [(token, flags, time_ms, logprob)])
+        self.enc = []          # encoder outputs, one per step
+        self.logits = []       # joiner logits, one per pass
+
+    def cb(self, r, toks):
+        self.log.append((int(r), [(t.token, t.flags, t.time_ms, round(t.logprob, 3)) for t in toks]))
+
+    def keys(self):
+        return [(r, [(a, b, c) for a, b, c, _ in toks]) for r, toks in self.log]
+
+    def finals(self):
+        return ["".join(t[0] for t in toks) for r, toks in self.log if r == 2]
+
+
+def chunk_iter(pcm, chunk):
+    if not chunk:
+        yield pcm
+        return
+    for i in range(0, len(pcm), chunk):
+        yield pcm[i:i + chunk]
+
+
+def run_oracle(model_file, pcm, chunk=None, tap=False, flush=True):
+    lib = oracle_lib()
+    m = A.Model(model_file, lib)
+    col = Collected()
+    keep = None
+    if tap:
+        def _tap(ud, net, data, n):
+            arr = np.ctypeslib.as_array(data, shape=(n,)).copy()
+            (col.enc if net == 0 else col.logits if net == 2 else []).append(arr)
+        keep = ORACLE_TAP(_tap)
+        lib.c.fake_ort_set_tap(ctypes.cast(keep, ctypes.c_void_p), None)
+    s = A.Session(m, col.cb)
+    for c in chunk_iter(pcm, chunk):
+        s.feed_pcm16(np.ascontiguousarray(c))
+    if flush:
+        s.flush()
+    if tap:
+        lib.c.fake_ort_set_tap(None, None)
+    s.close()
+    m.close()
+    return col
+
+
+def run_product_batch(model_file, pcms, chunk=None, tap=False, flush=True, model=None):
+    """All streams advance together through the batched entry points; returns one Collected per stream."""
+    lib = product_lib()
+    m = model or A.Model(model_file, lib)
+    cols = [Collected() for _ in pcms]
+    sessions = [A.Session(m, c.cb) for c in cols]
+    keep = None
+    if tap:
+        by_handle = {s.handle: c for s, c in zip(sessions, cols)}
+
+        def _tap(ud, sess, net, data, n):
+            arr = np.ctypeslib.as_array(data, shape=(n,)).copy()
+            c = by_handle[sess]
+            (c.enc if net == 0 else c.logits).append(arr)
+        keep = _ffi.TAP(_tap)
+        lib.c.aab_set_tap(m.handle, keep, None)
+    n = max(len(p) for p in pcms)
+    step = chunk or n
+    for i in range(0, n, step):
+        parts = [np.ascontiguousarray(p[i:i + step]) for p in pcms]
+        A.feed_pcm16_batch(sessions, parts)
+    if flush:
+        A.flush_batch(sessions)
+    if tap:
+        lib.c.aab_set_tap(m.handle, _ffi.TAP(0), None)
+    for s in sessions:
+        s.close()
+    if model is None:
+        m.close()
+    return cols
+
+
+def pcm_digest(pcm):
+    return hashlib.sha256(np.ascontiguousarray(pcm).tobytes()).hexdigest()[:16]
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)

@@ -1,0 +1,151 @@
+"""GPU parity tests (-m gpu): CUDA path through the C ABI vs the oracle / golden fixtures."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import april_asr_b200 as A
+import common as C
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-3      # stated fp32 tolerance on raw joiner logits / encoder_out (values are O(1..10))
+
+
+def test_fbank_rows_match_reference_golden():
+    g = np.load(os.path.join(C.GOLDEN, "fbank_stream0_3s.npz"))
+    pcm = C.gen_stream(0, 48000)
+    assert C.pcm_digest(pcm) == str(g["pcm_sha"])
+    lib = C.product_lib()
+    m = A.Model(C.TINY_MODEL, lib)
+    out = np.zeros((400, 80), np.float32)
+    n = lib.c.aab_debug_fbank(m.handle, pcm.ctypes.data_as(ctypes.POINTER(ctypes.c_short)), pcm.size,
+                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 400)
+    ref = g["rows"]
+    assert n == ref.shape[0]
+    diff = np.abs(out[:n] - ref)
+    mism = int((out[:n].view(np.uint32) != ref.view(np.uint32)).sum())
+    print("fbank: max abs diff %.3g, bit-mismatching values %d / %d" % (diff.max(), mism, ref.size))
+    assert diff.max() <= 2e-6           # fp64 FFT on device: expected bit-exact up to rare double-rounding
+    assert mism <= ref.size // 1000
+    m.close()
+
+
+@pytest.mark.parametrize("key", ["stream0", "stream1", "stream2", "stream3", "stream4"])
+def test_tokens_match_golden(key):
+    g = C.load_golden("tiny_callbacks.json")[key]
+    pcm = C.gen_stream(g["stream"], g["samples"]) if g["samples"] else np.zeros(0, np.int16)
+    assert C.pcm_digest(pcm) == g["pcm_sha"]
+    col = C.run_product_batch(C.TINY_MODEL, [pcm], chunk=g["chunk"])[0]
+    want = [(r, [(t, f, ms) for t, f, ms, lp in toks]) for r, toks in g["log"]]
+    assert col.keys() == want
+    got_lp = [lp for r, toks in col.log for _, _, _, lp in toks]
+    want_lp = [lp for r, toks in g["log"] for _, _, _, lp in toks]
+    assert np.allclose(got_lp, want_lp, atol=LOGIT_TOL)
+
+
+def test_batched_ragged_streams_match_oracle():
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    lens = [48000, 31000, 64000, 500, 0, 16000, 40000]
+    pcms = [C.gen_stream(20 + i, n) if n else np.zeros(0, np.int16) for i, n in enumerate(lens)]
+    cols = C.run_product_batch(C.TINY_MODEL, pcms, chunk=6400)
+    for p, c in zip(pcms, cols):
+        assert c.keys() == C.run_oracle(C.TINY_MODEL, p).keys()
+
+
+def test_encoder_out_and_logits_within_tolerance():
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    pcm = C.gen_stream(3, 80000)
+    o = C.run_oracle(C.TINY_MODEL, pcm, tap=True)
+    p = C.run_product_batch(C.TINY_MODEL, [pcm], tap=True)[0]
+    assert len(o.enc) == len(p.enc) and len(o.logits) == len(p.logits)
+    e = max(float(np.abs(a - b).max()) for a, b in zip(o.enc, p.enc))
+    l = max(float(np.abs(a - b).max()) for a, b in zip(o.logits, p.logits))
+    print("encoder_out max abs err %.3g, logits max abs err %.3g" % (e, l))
+    assert e < LOGIT_TOL and l < LOGIT_TOL
+    assert o.keys() == p.keys()
+
+
+def test_chunk_size_invariance_and_streaming_equals_bulk():
+    pcm = C.gen_stream(9, 64000)
+    base = C.run_product_batch(C.TINY_MODEL, [pcm])[0].keys()
+    for chunk in (640, 3200, 7001):
+        assert C.run_product_batch(C.TINY_MODEL, [pcm], chunk=chunk)[0].keys() == base
+
+
+def test_single_session_reference_api_and_flush_idempotence():
+    lib = C.product_lib()
+    m = A.Model(C.TINY_MODEL, lib)
+    assert m.get_sample_rate() == 16000 and m.get_language() == "en-us"
+    col = C.Collected()
+    s = A.Session(m, col.cb)
+    pcm = C.gen_stream(0, 96000)
+    s.feed_pcm16(pcm)
+    s.flush()
+    n = len(col.log)
+    s.flush()                                   # april_session.c:548-550
+    assert len(col.log) == n
+    g = C.load_golden("tiny_callbacks.json")["stream0"]
+    assert col.keys() == [(r, [(t, f, ms) for t, f, ms, lp in toks]) for r, toks in g["log"]]
+    assert s.get_rt_speedup() == 1.0
+    s.close()
+    m.close()
+
+
+def test_flush_on_fresh_session_and_feed_after_flush():
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    pcm = C.gen_stream(11, 40000)
+
+    def scenario(lib_kind):
+        lib = C.oracle_lib() if lib_kind == "o" else C.product_lib()
+        m = A.Model(C.TINY_MODEL, lib)
+        col = C.Collected()
+        s = A.Session(m, col.cb)
+        s.flush()                               # fresh flush: 25 padded steps
+        s.feed_pcm16(pcm[:20000]); s.flush()
+        s.feed_pcm16(pcm[20000:20100]); s.flush()   # < 512 new samples: avail_f stays below -27 until the zeros arrive
+        s.feed_pcm16(pcm[20100:]); s.flush()
+        s.close(); m.close()
+        return col.keys()
+    assert scenario("p") == scenario("o")
+
+
+def test_full_size_model_matches_oracle_tokens():
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    path = C.model_path("full")
+    pcms = [C.gen_stream(100 + i, 64000) for i in range(2)]
+    cols = C.run_product_batch(path, pcms, tap=True)
+    for pcm, c in zip(pcms, cols):
+        o = C.run_oracle(path, pcm, tap=True)
+        e = max(float(np.abs(a - b).max()) for a, b in zip(o.enc, c.enc))
+        print("full model: encoder_out max abs err %.3g over %d steps" % (e, len(o.enc)))
+        assert e < LOGIT_TOL
+        assert c.keys() == o.keys()
+
+
+def test_async_session_batcher():
+    import time
+    lib = C.product_lib()
+    m = A.Model(C.TINY_MODEL, lib)
+    cols = [C.Collected() for _ in range(4)]
+    ss = [A.Session(m, c.cb, asynchronous=True, no_rt=True) for c in cols]
+    pcms = [C.gen_stream(30 + i, 48000) for i in range(4)]
+    for i in range(0, 48000, 1600):
+        for s, p in zip(ss, pcms):
+            s.feed_pcm16(p[i:i + 1600])
+        time.sleep(0.002)
+    time.sleep(0.3)
+    for s in ss:
+        s.flush()
+    time.sleep(0.5)
+    sync = C.run_product_batch(C.TINY_MODEL, pcms, model=m)
+    for a, b in zip(cols, sync):
+        assert [k for k in a.keys() if k[0] != 3] == b.keys()
+    for s in ss:
+        s.close()
+    m.close()
