@@ -39,7 +39,7 @@ TAP = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, cty
 class AprilB200Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("encoder_steps", "joiner_passes", "decoder_runs", "frames", "kernel_launches",
                                                "h2d_bytes", "d2h_bytes")] + \
-               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms")]
+               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms", "compute_ms", "gemm_flops")] + [("gemm_launches", ctypes.c_uint64)]
 
 
 REFERENCE_SYMBOLS = [
@@ -49,7 +49,7 @@ REFERENCE_SYMBOLS = [
 ]
 B200_SYMBOLS = [
     "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_get_stats",
-    "aab_set_tap", "aab_engine_version", "aab_debug_fbank",
+    "aab_set_tap", "aab_engine_version", "aab_debug_fbank", "aab_set_timing", "aab_counting_handler",
 ]
 
 
@@ -85,5 +85,6 @@ class Lib:
             c.aab_debug_fbank.argtypes = [vp, ctypes.POINTER(ctypes.c_short), sz, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
             c.aab_debug_fbank.restype = ctypes.c_int
             c.aab_set_tap.argtypes, c.aab_set_tap.restype = [vp, TAP, vp], None
+            c.aab_set_timing.argtypes, c.aab_set_timing.restype = [vp, ctypes.c_int], None
             c.aab_get_stats.argtypes, c.aab_get_stats.restype = [vp, ctypes.POINTER(AprilB200Stats), ctypes.c_int], ctypes.c_int
         c.aam_api_init(1)

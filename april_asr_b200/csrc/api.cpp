@@ -321,12 +321,26 @@ APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int res
     out->encoder_steps = s.encoder_steps; out->joiner_passes = s.joiner_passes; out->decoder_runs = s.decoder_runs; out->frames = s.frames;
     out->kernel_launches = s.kernel_launches; out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
     out->device_ms = s.device_ms; out->lstm_scan_ms = s.lstm_scan_ms; out->gemm_ms = s.gemm_ms;
+    out->compute_ms = s.compute_ms; out->gemm_flops = s.gemm_flops; out->gemm_launches = s.gemm_launches;
     return 0;
 }
+
+APRIL_EXPORT void aab_set_timing(AprilASRModel model, int enabled) { if (model) model->engine->set_timing(enabled != 0); }
 
 APRIL_EXPORT void aab_set_tap(AprilASRModel model, AprilB200Tap tap, void* userdata) {
     if (!model) return;
     model->engine->set_tap(reinterpret_cast<TapFn>(tap), userdata);
+}
+
+// A ready-made handler for throughput measurements: userdata points at 4 uint64 counters
+// {partial calls, final calls, silence calls, tokens in final results}.
+APRIL_EXPORT void aab_counting_handler(void* userdata, AprilResultType type, size_t count, const AprilToken* tokens) {
+    (void)tokens;
+    uint64_t* c = static_cast<uint64_t*>(userdata);
+    if (!c) return;
+    if (type == APRIL_RESULT_RECOGNITION_PARTIAL) c[0]++;
+    else if (type == APRIL_RESULT_RECOGNITION_FINAL) { c[1]++; c[3] += count; }
+    else if (type == APRIL_RESULT_SILENCE) c[2]++;
 }
 
 APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t short_count, float* out_rows, int max_rows) {

@@ -76,6 +76,17 @@ public:
     TapFn tap = nullptr;
     void* tap_ud = nullptr;
     bool profile = false;
+    // per-kernel-class timing with CUDA events on the launching stream (no host syncs inside the pass)
+    struct Span { cudaEvent_t a, b; int cls; };
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<Span> spans;
+    cudaEvent_t ev_get() { if (ev_pool.empty()) { cudaEvent_t e; CK(cudaEventCreate(&e)); return e; } cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    void span_begin(int cls) { if (!profile) return; Span sp{ ev_get(), ev_get(), cls }; CK(cudaEventRecord(sp.a, st)); spans.push_back(sp); }
+    void span_end() { if (!profile) return; CK(cudaEventRecord(spans.back().b, st)); }
+    void spans_collect() {
+        for (auto& sp : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, sp.a, sp.b)); (sp.cls == 0 ? stat.gemm_ms : stat.lstm_scan_ms) += ms; ev_pool.push_back(sp.a); ev_pool.push_back(sp.b); }
+        spans.clear();
+    }
 
     // weights
     std::vector<void*> owned;
@@ -116,7 +127,7 @@ public:
         CK(cudaGetDeviceProperties(&prop, dev));
         if (prop.major != 10) { err = "this build targets sm_100a (B200); device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor); return false; }
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        profile = getenv("APRIL_B200_PROFILE") != nullptr;
+        profile = getenv("APRIL_B200_TIMING") != nullptr;
         if (d.D % 16 || d.H % 16 || d.F % 16 || d.J % 16 || (d.C3 * d.F3) % 16) { err = "model dims must be multiples of 16"; return false; }
 
         const ModelWeights& w = m.w;
@@ -275,6 +286,7 @@ public:
         return s;
     }
     void set_tap(TapFn fn, void* ud) override { std::lock_guard<std::mutex> lk(mu); tap = fn; tap_ud = ud; }
+    void set_timing(bool on) override { std::lock_guard<std::mutex> lk(mu); profile = on; }
     int stride_ms() const override { return prm.segment_step * prm.frame_shift_ms; }   // fbank.c:359-361
     int device() const override { return dev; }
 
@@ -305,6 +317,12 @@ public:
     void launch_check() { stat.kernel_launches++; CK(cudaGetLastError()); }
 
     void gemm(int epi, const float* A, const float* W, const float* bias, const float* R, float* C, int M, int N, int K) {
+        span_begin(0);
+        if (profile) { stat.gemm_flops += 2.0 * (double)M * (double)N * (double)K; stat.gemm_launches++; }
+        gemm_launch(epi, A, W, bias, R, C, M, N, K);
+        span_end();
+    }
+    void gemm_launch(int epi, const float* A, const float* W, const float* bias, const float* R, float* C, int M, int N, int K) {
         dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
         if (epi == k::EPI_BIAS) k::gemm_simt_kernel<k::EPI_BIAS><<<grid, 256, 0, st>>>(A, W, bias, R, C, M, N, K);
         else if (epi == k::EPI_BIAS_DSWISH) k::gemm_simt_kernel<k::EPI_BIAS_DSWISH><<<grid, 256, 0, st>>>(A, W, bias, R, C, M, N, K);
@@ -383,9 +401,7 @@ public:
             if (consumed > n_buf) consumed = n_buf;
             fr.tail.assign(dst + consumed, dst + n_buf);
         }
-        auto t_host = std::chrono::steady_clock::now();
-        cudaEvent_t ev0, ev1;
-        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+        cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
         CK(cudaEventRecord(ev0, st));
         b_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
         if (pcm_total) CK(cudaMemcpyAsync(b_pcm.p, hp, pcm_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
@@ -412,6 +428,7 @@ public:
             *d_flush = dm + 6 * nI, *d_keepf = dm + 7 * nI, *d_nkeep = dm + 8 * nI;
         long long* d_off = reinterpret_cast<long long*>(dm + 9 * nI + (nI & 1));
 
+        CK(cudaEventRecord(evc, st));     // uploads done: what follows is the device-resident part of the pass
         // ---- front-end ------------------------------------------------------------------------------
         b_fb.ensure(sizeof(float) * (size_t)B * row_pitch * MEL);
         float* FB = b_fb.as<float>();
@@ -421,7 +438,6 @@ public:
             k::fbank_kernel<<<grid, 128, (size_t)4 * 3 * N * sizeof(double), st>>>(fp, b_pcm.as<int16_t>(), d_off, d_padb, d_nfr, d_nnew, d_carry, FB, row_pitch);
             launch_check();
         }
-        double ms_front = profile ? sync_ms_since(t_host) : 0;
 
         // ---- encoder + search, in time chunks -------------------------------------------------------
         size_t rec_bytes = 0, np_bytes = 0;
@@ -451,12 +467,10 @@ public:
                 k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, M, D, out_norm_eps); launch_check();
                 for (int l = 0; l < L; l++) {
                     const DeviceLayer& w = layers[(size_t)l];
-                    auto tg = std::chrono::steady_clock::now();
-                    if (profile) CK(cudaStreamSynchronize(st));
                     gemm(k::EPI_BIAS, X, w.w_ih, w.b_gate, nullptr, G, M, 4 * H, D);
-                    if (profile) stat.gemm_ms += sync_ms_since(tg);
                     float* hw = Hw + (size_t)l * B * D;
                     float* cw = Cw + (size_t)l * B * H;
+                    span_begin(1);
                     for (int t = 0; t < tc; t++) {
                         k::lstm_gates_kernel<<<dim3((unsigned)(H / 16), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
                             G + (size_t)t * B * 4 * H, hw, w.w_hh, cw, Ms, d_nsteps, t0 + t, B, D, H);
@@ -465,13 +479,12 @@ public:
                             Ms, w.w_hr, hw, Hout + (size_t)t * B * D, d_nsteps, t0 + t, B, D, H);
                         launch_check();
                     }
-                    if (profile) stat.lstm_scan_ms += sync_ms_since(tg);
+                    span_end();
                     k::add_rows_kernel<<<(unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, 148 * 8), 256, 0, st>>>(
                         reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Hout), reinterpret_cast<float4*>(X1), (size_t)M * D / 4);
                     launch_check();
                     gemm(k::EPI_BIAS_DSWISH, X1, w.ff1_w, w.ff1_b, nullptr, F1, M, F, D);
                     gemm(k::EPI_BIAS_RESIDUAL, F1, w.ff2_w, w.ff2_b, X1, X2, M, D, F);
-                    if (profile) stat.gemm_ms += sync_ms_since(tg);
                     k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
                 }
                 gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
@@ -506,8 +519,10 @@ public:
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stat.device_ms += ms;
-        CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
-        (void)ms_front;
+        CK(cudaEventElapsedTime(&ms, evc, ev1));
+        stat.compute_ms += ms;
+        ev_pool.push_back(ev0); ev_pool.push_back(ev1); ev_pool.push_back(evc);
+        spans_collect();
 
         // ---- hand decisions back ----------------------------------------------------------------------
         const k::DecisionRecord* hr = p_rec.as<k::DecisionRecord>();

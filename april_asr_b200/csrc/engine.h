@@ -44,7 +44,8 @@ struct PassItem {
 
 struct EngineStats {
     uint64_t encoder_steps = 0, joiner_passes = 0, decoder_runs = 0, frames = 0, kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-    double device_ms = 0, lstm_scan_ms = 0, gemm_ms = 0;
+    double device_ms = 0, lstm_scan_ms = 0, gemm_ms = 0, compute_ms = 0, gemm_flops = 0;
+    uint64_t gemm_launches = 0;
 };
 
 typedef void (*TapFn)(void* userdata, void* cookie, int net, const float* data, size_t n);
@@ -58,6 +59,7 @@ public:
     virtual void run_pass(std::vector<PassItem>& items) = 0;   // aborts on CUDA errors (ORT_ABORT_ON_ERROR convention)
     virtual EngineStats stats(bool reset) = 0;
     virtual void set_tap(TapFn fn, void* userdata) = 0;
+    virtual void set_timing(bool on) = 0;
     // test hook: log-mel rows of one standalone stream (frames [160 i, 160 i + N)), returns the row count
     virtual int debug_fbank(const int16_t* pcm, size_t n, float* out_rows, int max_rows) = 0;
     virtual int stride_ms() const = 0;

@@ -50,10 +50,15 @@ typedef struct AprilB200Stats {
     double   device_ms;         /* CUDA-event time of all engine passes */
     double   lstm_scan_ms;      /* ... of which the recurrent scan kernels */
     double   gemm_ms;           /* ... of which the time-batched GEMMs */
+    double   compute_ms;        /* device_ms minus the host->device upload at the head of each pass */
+    double   gemm_flops;        /* algorithmic FLOPs (2 M N K) of the GEMM launches timed in gemm_ms */
+    uint64_t gemm_launches;
 } AprilB200Stats;
 
-/* Cumulative statistics of a model's engine; reset != 0 zeroes them after reading. */
+/* Cumulative statistics of a model's engine; reset != 0 zeroes them after reading. lstm_scan_ms / gemm_ms /
+ * gemm_flops are only collected while per-kernel-class CUDA-event timing is on (aab_set_timing). */
 APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int reset);
+APRIL_EXPORT void aab_set_timing(AprilASRModel model, int enabled);
 
 /* Debug/parity tap: after every engine pass, called once per session-step with the encoder output
  * (net = 0, n = joiner dim) and once per joiner pass with the raw logits (net = 2, n = vocab) —
@@ -61,6 +66,10 @@ APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int res
  * (src/april_session.c:145,176). Costs extra device->host traffic; NULL disables. */
 typedef void (*AprilB200Tap)(void* userdata, AprilASRSession session, int net, const float* data, size_t n);
 APRIL_EXPORT void aab_set_tap(AprilASRModel model, AprilB200Tap tap, void* userdata);
+
+/* A handler (AprilRecognitionResultHandler signature) that only counts: userdata -> uint64_t[4]
+ * {partial calls, final calls, silence calls, tokens delivered in final results}. */
+APRIL_EXPORT void aab_counting_handler(void* userdata, AprilResultType type, size_t count, const AprilToken* tokens);
 
 /* Test hook: run only the front-end kernel (F1/F2, src/fbank.c:174-306) on one standalone stream and
  * return its log-mel rows ([rows][mel_features] floats). Returns the number of rows written. */

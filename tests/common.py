@@ -121,7 +121,7 @@ def run_product_batch(model_file, pcms, chunk=None, tap=False, flush=True, model
         keep = _ffi.TAP(_tap)
         lib.c.aab_set_tap(m.handle, keep, None)
     n = max(len(p) for p in pcms)
-    step = chunk or n
+    step = chunk or max(n, 1)
     for i in range(0, n, step):
         parts = [np.ascontiguousarray(p[i:i + step]) for p in pcms]
         A.feed_pcm16_batch(sessions, parts)
