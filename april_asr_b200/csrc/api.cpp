@@ -348,4 +348,9 @@ APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t
     return model->engine->debug_fbank(pcm16, short_count, out_rows, max_rows);
 }
 
+APRIL_EXPORT int aab_debug_gemm(AprilASRModel model, int tier, int M, int N, int K, const float* A, const float* W, const float* bias, float* out) {
+    if (!model || !A || !W || !bias || !out) return -1;
+    return model->engine->debug_gemm(tier, M, N, K, A, W, bias, out);
+}
+
 }  // extern "C"

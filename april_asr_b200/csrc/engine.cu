@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 
 namespace april {
 
@@ -23,6 +24,39 @@ namespace april {
     } while (0)
 
 namespace {
+
+// ---- TMA descriptors (driver entry point fetched through the runtime; no -lcuda at link time) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled unavailable\n"); abort(); }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// [rows, cols] fp16 row-major (cols contiguous = K); box = 64 x box_rows, 128-byte swizzle
+static CUtensorMap make_map_f16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = { cols, rows };
+    cuuint64_t strides[1] = { cols * sizeof(__half) };
+    cuuint32_t box[2] = { 64, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled failed: %d (rows %llu cols %llu)\n", (int)r, (unsigned long long)rows, (unsigned long long)cols); abort(); }
+    return m;
+}
+
+struct TcWeight {                   // fp16 (hi, lo) copies of a [N, K] weight, pre-scaled by a power of two
+    __half *hi = nullptr, *lo = nullptr;
+    float inv_scale = 1.f;
+    int N = 0, K = 0;
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -70,6 +104,7 @@ public:
     ModelDims d;
     Params prm;
     int dev = 0;
+    int num_sms = 148;
     cudaStream_t st = nullptr;
     std::mutex mu;
     EngineStats stat;
@@ -93,6 +128,11 @@ public:
     float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *conv3_w, *conv3_b, *out_w, *out_b, *enc_proj_w, *enc_proj_b;
     float out_norm_eps = 0.f;
     std::vector<DeviceLayer> layers;
+    int npass = 3;                  // 0: exact fp32 SIMT tier; 1: fp16 tensor cores; 3: fp16x3 split (default)
+    TcWeight tw_out, tw_proj;
+    struct TcLayer { TcWeight w_ih, ff1, ff2; };
+    std::vector<TcLayer> tlayers;
+    DevBuf b_xe_h, b_xe_l, b_x_h, b_x_l, b_x1_h, b_x1_l, b_f1_h, b_f1_l;
     k::JoinerParams jp{};
     k::FbankParams fp{};
     k::ConvParams cp{};
@@ -127,6 +167,7 @@ public:
         CK(cudaGetDeviceProperties(&prop, dev));
         if (prop.major != 10) { err = "this build targets sm_100a (B200); device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor); return false; }
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        num_sms = prop.multiProcessorCount;
         profile = getenv("APRIL_B200_TIMING") != nullptr;
         if (d.D % 16 || d.H % 16 || d.F % 16 || d.J % 16 || (d.C3 * d.F3) % 16) { err = "model dims must be multiples of 16"; return false; }
 
@@ -145,6 +186,23 @@ public:
             layers.push_back(dl);
         }
         enc_proj_w = upload(w.enc_proj_w); enc_proj_b = upload(w.enc_proj_b);
+        if (const char* pm = getenv("APRIL_B200_PRECISION")) {
+            if (!strcmp(pm, "fp32")) npass = 0; else if (!strcmp(pm, "fp16")) npass = 1; else if (!strcmp(pm, "fp16x3")) npass = 3;
+            else { err = "APRIL_B200_PRECISION must be fp32, fp16 or fp16x3"; return false; }
+        }
+        if (npass) {
+            if (d.D % 8 || d.H % 8 || d.F % 8 || d.J % 8) { err = "tensor-core tier needs dims that are multiples of 8"; return false; }
+            tw_out = make_tc_weight(w.out_w, d.D, d.C3 * d.F3);
+            tw_proj = make_tc_weight(w.enc_proj_w, d.J, d.D);
+            for (auto& lw : w.layers) {
+                TcLayer tl;
+                tl.w_ih = make_tc_weight(lw.w_ih, 4 * d.H, d.D);
+                tl.ff1 = make_tc_weight(lw.ff1_w, d.F, d.D);
+                tl.ff2 = make_tc_weight(lw.ff2_w, d.D, d.F);
+                tlayers.push_back(tl);
+            }
+            set_gemm_attrs();
+        }
 
         // vocabulary flags (april_session.c:338-351)
         std::vector<uint8_t> vf((size_t)d.V, 0);
@@ -289,6 +347,85 @@ public:
     void set_timing(bool on) override { std::lock_guard<std::mutex> lk(mu); profile = on; }
     int stride_ms() const override { return prm.segment_step * prm.frame_shift_ms; }   // fbank.c:359-361
     int device() const override { return dev; }
+
+    TcWeight make_tc_weight(const std::vector<float>& w, int N, int K) {
+        TcWeight t; t.N = N; t.K = K;
+        float mx = 0.f;
+        for (float v : w) mx = std::max(mx, std::fabs(v));
+        int e = mx > 0.f ? (int)std::floor(std::log2(1024.0 / (double)mx)) : 0;      // max |w| * 2^e in [512, 1024]
+        e = std::max(-24, std::min(24, e));
+        const float sc = std::ldexp(1.0f, e);
+        t.inv_scale = std::ldexp(1.0f, -e);
+        std::vector<__half> hi(w.size()), lo(w.size());
+        for (size_t i = 0; i < w.size(); i++) {
+            float x = w[i] * sc;                       // exact (power of two)
+            __half h = __float2half_rn(x);
+            hi[i] = h; lo[i] = __float2half_rn(x - __half2float(h));
+        }
+        t.hi = upload(hi); t.lo = upload(lo);
+        return t;
+    }
+
+    void set_gemm_attrs() {
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_DSWISH_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_DSWISH_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
+    }
+
+    // C = A * W^T (+bias, epilogue) on the tensor cores. A given as fp16 (hi, lo) [M, K].
+    void gemm_tc(int epi, const __half* a_hi, const __half* a_lo, const TcWeight& w, const float* bias, const float* residual,
+                 float* out_f32, __half* out_hi, __half* out_lo, int M) {
+        span_begin(0);
+        if (profile) { stat.gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; stat.gemm_launches++; }
+        CUtensorMap mAh = make_map_f16(a_hi, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM), mAl = make_map_f16(a_lo, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM);
+        CUtensorMap mBh = make_map_f16(w.hi, (uint64_t)w.N, (uint64_t)w.K, tc::GEMM_BN), mBl = make_map_f16(w.lo, (uint64_t)w.N, (uint64_t)w.K, tc::GEMM_BN);
+        tc::GemmArgs g{ M, w.N, w.K, w.inv_scale, bias, residual, out_f32, out_hi, out_lo };
+        const int tiles = ((M + tc::GEMM_BM - 1) / tc::GEMM_BM) * ((w.N + tc::GEMM_BN - 1) / tc::GEMM_BN);
+        const unsigned grid = (unsigned)std::min(tiles, num_sms);
+        if (npass == 3) {
+            const size_t sm = tc::GemmCfg<3>::SMEM_BYTES;
+            if (epi == tc::GE_F32) tc::gemm_tc_kernel<3, tc::GE_F32><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            else tc::gemm_tc_kernel<3, tc::GE_DSWISH_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+        } else {
+            const size_t sm = tc::GemmCfg<1>::SMEM_BYTES;
+            if (epi == tc::GE_F32) tc::gemm_tc_kernel<1, tc::GE_F32><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            else tc::gemm_tc_kernel<1, tc::GE_DSWISH_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+        }
+        launch_check();
+        span_end();
+    }
+
+    // test hook: out[M,N] = A[M,K] W[N,K]^T + bias through the selected tier (0 = SIMT fp32, 1 = fp16, 3 = fp16x3)
+    int debug_gemm(int tier, int M, int N, int K, const float* A, const float* W, const float* bias, float* out) override {
+        std::lock_guard<std::mutex> lk(mu);
+        CK(cudaSetDevice(dev));
+        DevBuf dA, dW, dB, dO, dAh, dAl;
+        dA.ensure(sizeof(float) * (size_t)M * K); dW.ensure(sizeof(float) * (size_t)N * K); dB.ensure(sizeof(float) * (size_t)N); dO.ensure(sizeof(float) * (size_t)M * N);
+        CK(cudaMemcpyAsync(dA.p, A, sizeof(float) * (size_t)M * K, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dW.p, W, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dB.p, bias, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+        if (tier == 0) gemm_launch(k::EPI_BIAS, dA.as<float>(), dW.as<float>(), dB.as<float>(), nullptr, dO.as<float>(), M, N, K);
+        else {
+            if (K % 8 || N % 8) return -1;
+            const int saved = npass;
+            npass = tier; set_gemm_attrs();
+            std::vector<float> wv(W, W + (size_t)N * K);
+            TcWeight tw = make_tc_weight(wv, N, K);
+            dAh.ensure(sizeof(__half) * (size_t)M * K); dAl.ensure(sizeof(__half) * (size_t)M * K);
+            tc::split_rows_kernel<<<(unsigned)std::min<size_t>(((size_t)M * K / 4 + 255) / 256, 148 * 8), 256, 0, st>>>(dA.as<float>(), dAh.as<__half>(), dAl.as<__half>(), (size_t)M * K);
+            launch_check();
+            gemm_tc(tc::GE_F32, dAh.as<__half>(), dAl.as<__half>(), tw, dB.as<float>(), nullptr, dO.as<float>(), nullptr, nullptr, M);
+            npass = saved;
+        }
+        CK(cudaMemcpyAsync(out, dO.p, sizeof(float) * (size_t)M * N, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
 
     int debug_fbank(const int16_t* pcm, size_t n, float* out_rows, int max_rows) override {
         std::lock_guard<std::mutex> lk(mu);
@@ -451,6 +588,14 @@ public:
             b_g.ensure(sizeof(float) * Mc * 4 * H); b_hout.ensure(sizeof(float) * Mc * D); b_f1.ensure(sizeof(float) * Mc * F);
             b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
             b_eo.ensure(sizeof(float) * Mc * J);
+            if (npass) {
+                b_xe_h.ensure(sizeof(__half) * Mc * KE); b_xe_l.ensure(sizeof(__half) * Mc * KE);
+                b_x_h.ensure(sizeof(__half) * Mc * D); b_x_l.ensure(sizeof(__half) * Mc * D);
+                b_x1_h.ensure(sizeof(__half) * Mc * D); b_x1_l.ensure(sizeof(__half) * Mc * D);
+                b_f1_h.ensure(sizeof(__half) * Mc * F); b_f1_l.ensure(sizeof(__half) * Mc * F);
+            }
+            __half *Xe_h = b_xe_h.as<__half>(), *Xe_l = b_xe_l.as<__half>(), *X_h = b_x_h.as<__half>(), *X_l = b_x_l.as<__half>(), *X1_h = b_x1_h.as<__half>(),
+                   *X1_l = b_x1_l.as<__half>(), *F1_h = b_f1_h.as<__half>(), *F1_l = b_f1_l.as<__half>();
             rec_bytes = sizeof(k::DecisionRecord) * (size_t)B * Tmax * 3; np_bytes = sizeof(int) * (size_t)B * Tmax;
             b_rec.ensure(rec_bytes); b_np.ensure(np_bytes);
             if (want_tap) { b_tap.ensure(sizeof(float) * (size_t)B * Tmax * 3 * d.V); p_tap.ensure(sizeof(float) * (size_t)B * Tmax * 3 * d.V); p_eo.ensure(sizeof(float) * (size_t)Tmax * B * J); }
@@ -463,11 +608,19 @@ public:
                 const int tc = std::min(Tc, Tmax - t0);
                 const int M = tc * B;
                 k::conv_embed_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(cp, FB, row_pitch, d_nsteps, t0, B, Xe); launch_check();
-                gemm(k::EPI_BIAS, Xe, out_w, out_b, nullptr, X1, M, D, KE);
-                k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, M, D, out_norm_eps); launch_check();
+                const unsigned ew_grid = (unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, (size_t)num_sms * 8);
+                if (npass == 0) {
+                    gemm(k::EPI_BIAS, Xe, out_w, out_b, nullptr, X1, M, D, KE);
+                    k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, M, D, out_norm_eps); launch_check();
+                } else {
+                    tc::split_rows_kernel<<<(unsigned)std::min<size_t>(((size_t)M * KE / 4 + 255) / 256, (size_t)num_sms * 8), 256, 0, st>>>(Xe, Xe_h, Xe_l, (size_t)M * KE); launch_check();
+                    gemm_tc(tc::GE_F32, Xe_h, Xe_l, tw_out, out_b, nullptr, X1, nullptr, nullptr, M);
+                    tc::basic_norm_split_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, X_h, X_l, M, D, out_norm_eps); launch_check();
+                }
                 for (int l = 0; l < L; l++) {
                     const DeviceLayer& w = layers[(size_t)l];
-                    gemm(k::EPI_BIAS, X, w.w_ih, w.b_gate, nullptr, G, M, 4 * H, D);
+                    if (npass == 0) gemm(k::EPI_BIAS, X, w.w_ih, w.b_gate, nullptr, G, M, 4 * H, D);
+                    else gemm_tc(tc::GE_F32, X_h, X_l, tlayers[(size_t)l].w_ih, w.b_gate, nullptr, G, nullptr, nullptr, M);
                     float* hw = Hw + (size_t)l * B * D;
                     float* cw = Cw + (size_t)l * B * H;
                     span_begin(1);
@@ -480,14 +633,22 @@ public:
                         launch_check();
                     }
                     span_end();
-                    k::add_rows_kernel<<<(unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, 148 * 8), 256, 0, st>>>(
-                        reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Hout), reinterpret_cast<float4*>(X1), (size_t)M * D / 4);
-                    launch_check();
-                    gemm(k::EPI_BIAS_DSWISH, X1, w.ff1_w, w.ff1_b, nullptr, F1, M, F, D);
-                    gemm(k::EPI_BIAS_RESIDUAL, F1, w.ff2_w, w.ff2_b, X1, X2, M, D, F);
-                    k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
+                    if (npass == 0) {
+                        k::add_rows_kernel<<<ew_grid, 256, 0, st>>>(reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Hout), reinterpret_cast<float4*>(X1), (size_t)M * D / 4);
+                        launch_check();
+                        gemm(k::EPI_BIAS_DSWISH, X1, w.ff1_w, w.ff1_b, nullptr, F1, M, F, D);
+                        gemm(k::EPI_BIAS_RESIDUAL, F1, w.ff2_w, w.ff2_b, X1, X2, M, D, F);
+                        k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
+                    } else {
+                        const TcLayer& tl = tlayers[(size_t)l];
+                        tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check();
+                        gemm_tc(tc::GE_DSWISH_SPLIT, X1_h, X1_l, tl.ff1, w.ff1_b, nullptr, nullptr, F1_h, F1_l, M);
+                        gemm_tc(tc::GE_F32_RESIDUAL, F1_h, F1_l, tl.ff2, w.ff2_b, X1, X2, nullptr, nullptr, M);
+                        tc::basic_norm_split_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, X_h, X_l, M, D, w.norm_eps); launch_check();
+                    }
                 }
-                gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
+                if (npass == 0) gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
+                else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
                 k::greedy_kernel<<<B, 256, greedy_smem, st>>>(jp, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate, dout_store, dout_blank,
                                                              b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc);

@@ -62,6 +62,7 @@ public:
     virtual void set_timing(bool on) = 0;
     // test hook: log-mel rows of one standalone stream (frames [160 i, 160 i + N)), returns the row count
     virtual int debug_fbank(const int16_t* pcm, size_t n, float* out_rows, int max_rows) = 0;
+    virtual int debug_gemm(int tier, int M, int N, int K, const float* A, const float* W, const float* bias, float* out) = 0;
     virtual int stride_ms() const = 0;
     virtual int device() const = 0;
 };

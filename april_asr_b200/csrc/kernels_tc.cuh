@@ -1,0 +1,338 @@
+// Tensor-core tier for sm_100a: tcgen05.mma (UMMA) fed by TMA into 128B-swizzled shared memory,
+// fp32 accumulators in TMEM, warp-specialised persistent CTAs. All PTX is written by hand here.
+//
+// Numerics: the reference path is fp32 (ONNXRuntime CPU). To keep emitted tokens identical while
+// using the fp16 tensor pipe, every operand x is carried as an fp16 pair (hi, lo) with
+// hi = fp16(x), lo = fp16(x - hi) (22-23 significant bits), weights pre-scaled by a power of two so
+// that lo never underflows, and each product is issued as three MMAs
+//     A_hi*B_lo + A_lo*B_hi + A_hi*B_hi            (the dropped lo*lo term is < 2^-22 relative)
+// accumulated in fp32 in TMEM ("fp16x3"). NPASS = 1 issues only A_hi*B_hi (plain fp16 inputs).
+// The four sub-tiles of a k-block are loaded ONCE per stage and used by all three MMA groups, so
+// the split costs 3x tensor work but only 2x shared-memory fill (64 MAC/B at 128x256x64 tiles).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace april {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t_start = clock64();
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if ((spin & 0xFFFF) == 0xFFFF && clock64() - t_start > 4000000000LL) { printf("libapril: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i of the warp receives lane (quarter base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle (what TMA SWIZZLE_128B writes for a
+// [rows x 64 fp16] box): 8-row groups of 1024 B (SBO), LBO unused, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                              // version = 1
+    d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float dswish_f(float x) { return x * sigmoid_f(x - 1.0f); }
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM  C[M,N] = (sum_p A_p[M,K] * B_p[N,K]^T) * inv_scale + bias  (+ epilogue)
+// ------------------------------------------------------------------------------------------------
+enum GemmEpi { GE_F32 = 0,            // out_f32 = v
+               GE_F32_RESIDUAL = 1,   // out_f32 = v + R
+               GE_DSWISH_SPLIT = 2 }; // (out_hi, out_lo) = split(double_swish(v))
+
+struct GemmArgs {
+    int M, N, K;
+    float inv_scale;
+    const float* bias;        // [N] or null
+    const float* residual;    // [M,N] fp32 (GE_F32_RESIDUAL)
+    float* out_f32;           // [M,N]
+    __half* out_hi;           // [M,N]
+    __half* out_lo;
+};
+
+constexpr int GEMM_BM = 128, GEMM_BN = 256, GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+
+template <int NPASS> struct GemmCfg {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;                    // 16 KB
+    static constexpr int B_BYTES = GEMM_BN * GEMM_BK * 2;                    // 32 KB
+    static constexpr int STAGE_BYTES = (NPASS == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = NPASS == 3 ? 2 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int NPASS, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, GemmArgs g) {
+    using Cfg = GemmCfg<NPASS>;
+    constexpr int S = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + S * Cfg::STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2], tmem slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (g.N + GEMM_BN - 1) / GEMM_BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int nkb = (g.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
+            if (NPASS == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % S; const uint32_t ph = (it / S) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                    tma_load_2d(st, &mapAhi, full_bar(s), kb * GEMM_BK, m0);
+                    tma_load_2d(st + Cfg::A_BYTES, &mapBhi, full_bar(s), kb * GEMM_BK, n0);
+                    if (NPASS == 3) {
+                        tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mapAlo, full_bar(s), kb * GEMM_BK, m0);
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, full_bar(s), kb * GEMM_BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, GEMM_BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+                const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
+                mbar_wait(tempty_bar(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % S; const uint32_t ph = (it / S) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+                    const uint64_t ahi = make_sw128_desc(st), bhi = make_sw128_desc(st + Cfg::A_BYTES);
+                    if (NPASS == 3) {
+                        const uint64_t alo = make_sw128_desc(st + Cfg::A_BYTES + Cfg::B_BYTES), blo = make_sw128_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(s));             // smem stage free once these MMAs have read it
+                }
+                umma_commit(tfull_bar(acc));               // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+            const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
+            const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < GEMM_BN / 32; c++) {
+                const int nb = n0 + c * 32;
+                if (nb >= g.N) break;                      // warp-uniform
+                float v[32];
+                tmem_ld32(tmem_base + acc * GEMM_BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                if (m < g.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (nb + j >= g.N) break;
+                        float x[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) x[e] = v[j + e] * g.inv_scale + (g.bias ? __ldg(g.bias + nb + j + e) : 0.f);
+                        const size_t off = (size_t)m * g.N + nb + j;
+                        if (EPI == GE_F32 || EPI == GE_F32_RESIDUAL) {
+                            if (EPI == GE_F32_RESIDUAL) {
+                                const float4 r0 = *reinterpret_cast<const float4*>(g.residual + off), r1 = *reinterpret_cast<const float4*>(g.residual + off + 4);
+                                x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w; x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+                            }
+                            *reinterpret_cast<float4*>(g.out_f32 + off) = make_float4(x[0], x[1], x[2], x[3]);
+                            *reinterpret_cast<float4*>(g.out_f32 + off + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                        } else {
+                            __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) split_f16(dswish_f(x[e]), hi[e], lo[e]);
+                            *reinterpret_cast<uint4*>(g.out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+                            *reinterpret_cast<uint4*>(g.out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise helpers that also produce the fp16 (hi, lo) operand copies for the next GEMM
+// ------------------------------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        float4 v = *reinterpret_cast<const float4*>(x + i);
+        __align__(8) __half h[4], l[4];
+        split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+
+// y = a + b, plus split copies
+__global__ void add_rows_split_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                      __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        float4 p = *reinterpret_cast<const float4*>(a + i), q = *reinterpret_cast<const float4*>(b + i);
+        float4 v = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+        *reinterpret_cast<float4*>(y + i) = v;
+        __align__(8) __half h[4], l[4];
+        split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+
+// BasicNorm (one warp per row) writing fp32 and split copies
+__global__ void basic_norm_split_kernel(const float* __restrict__ X, float* __restrict__ Y, __half* __restrict__ hi, __half* __restrict__ lo,
+                                        int M, int D, float eps) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* x = X + (size_t)row * D;
+    float s = 0.f;
+    for (int i = lane; i < D; i += 32) s = fmaf(x[i], x[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float scale = 1.0f / sqrtf(s / (float)D + eps);
+    for (int i = lane; i < D; i += 32) {
+        float v = x[i] * scale;
+        Y[(size_t)row * D + i] = v;
+        __half h, l; split_f16(v, h, l);
+        hi[(size_t)row * D + i] = h; lo[(size_t)row * D + i] = l;
+    }
+}
+
+}  // namespace tc
+}  // namespace april

@@ -75,6 +75,10 @@ APRIL_EXPORT void aab_counting_handler(void* userdata, AprilResultType type, siz
  * return its log-mel rows ([rows][mel_features] floats). Returns the number of rows written. */
 APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t short_count, float* out_rows, int max_rows);
 
+/* Test hook: out[M,N] = A[M,K] * W[N,K]^T + bias[N] through one GEMM tier of the engine
+ * (tier 0 = fp32 SIMT, 1 = fp16 tcgen05, 3 = fp16x3 split tcgen05). Host pointers. */
+APRIL_EXPORT int aab_debug_gemm(AprilASRModel model, int tier, int M, int N, int K, const float* A, const float* W, const float* bias, float* out);
+
 APRIL_EXPORT const char* aab_engine_version(void);
 
 #ifdef __cplusplus
