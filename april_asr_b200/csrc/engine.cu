@@ -11,6 +11,7 @@
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_scan.cuh"
 
 namespace april {
 
@@ -49,6 +50,19 @@ static CUtensorMap make_map_f16(const void* ptr, uint64_t rows, uint64_t cols, u
     CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled failed: %d (rows %llu cols %llu)\n", (int)r, (unsigned long long)rows, (unsigned long long)cols); abort(); }
+    return m;
+}
+
+// generic 2-D map: [rows, cols] row-major of `esize`-byte elements, box = box_cols x box_rows
+static CUtensorMap make_map_2d(const void* ptr, CUtensorMapDataType dt, size_t esize, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows, bool swizzle128) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = { cols, rows };
+    cuuint64_t strides[1] = { cols * esize };
+    cuuint32_t box[2] = { box_cols, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = get_encode_tiled()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled failed: %d\n", (int)r); abort(); }
     return m;
 }
 
@@ -132,6 +146,13 @@ public:
     TcWeight tw_out, tw_proj;
     struct TcLayer { TcWeight w_ih, ff1, ff2; };
     std::vector<TcLayer> tlayers;
+    // persistent tensor-core scan: stacked (hi;lo) recurrent weights per layer + exchange buffers
+    struct ScanLayer { __half *wg = nullptr, *wp = nullptr; float inv_hh = 1.f, inv_hr = 1.f; CUtensorMap mapWg, mapWp; };
+    std::vector<ScanLayer> slayers;
+    bool scan_tc = false;
+    __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
+    unsigned* scan_counters = nullptr;
+    size_t scan_smem = 0;
     DevBuf b_xe_h, b_xe_l, b_x_h, b_x_l, b_x1_h, b_x1_l, b_f1_h, b_f1_l;
     k::JoinerParams jp{};
     k::FbankParams fp{};
@@ -202,6 +223,7 @@ public:
                 tlayers.push_back(tl);
             }
             set_gemm_attrs();
+            init_scan(w);
         }
 
         // vocabulary flags (april_session.c:338-351)
@@ -364,6 +386,92 @@ public:
         }
         t.hi = upload(hi); t.lo = upload(lo);
         return t;
+    }
+
+    static void stack_hi_lo(const std::vector<float>& rows_src, size_t K, float sc, __half* dst_hi, __half* dst_lo) {
+        for (size_t i = 0; i < rows_src.size(); i++) {
+            float x = rows_src[i] * sc;
+            __half h = __float2half_rn(x);
+            dst_hi[i] = h; dst_lo[i] = __float2half_rn(x - __half2float(h));
+        }
+        (void)K;
+    }
+    static float pow2_scale(const std::vector<float>& w, float& inv) {
+        float mx = 0.f;
+        for (float v : w) mx = std::max(mx, std::fabs(v));
+        int e = mx > 0.f ? (int)std::floor(std::log2(1024.0 / (double)mx)) : 0;
+        e = std::max(-24, std::min(24, e));
+        inv = std::ldexp(1.0f, -e);
+        return std::ldexp(1.0f, e);
+    }
+
+    // Stacked recurrent weights for lstm_scan_tc_kernel: per gate CTA c, 128 rows = [hi of rows {g*H + 16c + u}; lo of the same],
+    // per projection slice r, 64 rows = [hi of W_hr rows 32r..32r+31 ; lo of the same].
+    void init_scan(const ModelWeights& w) {
+        const int D = d.D, H = d.H;
+        const int GC = H / scan::UNITS, RS = D / scan::PROWS;
+        scan_tc = (D % 64 == 0) && (H % 64 == 0) && (H % scan::UNITS == 0) && (D % scan::PROWS == 0) && (GC + RS * 4 <= num_sms) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
+        if (!scan_tc) return;
+        const size_t wbytes = std::max<size_t>((size_t)(D / 64) * 16384, (size_t)(H / 64) * 8192);
+        scan_smem = 1024 + wbytes + std::max<size_t>((size_t)scan::NSTAGE * 64 * 128, (size_t)128 * 65 * 4) + 1024 + 2 * (size_t)64 * 16 * 16 + (size_t)64 * scan::UNITS * 4 + 512;
+        if (scan_smem > 227 * 1024) { scan_tc = false; return; }
+        CK(cudaFuncSetAttribute(scan::lstm_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+        for (auto& lw : w.layers) {
+            ScanLayer sl;
+            float sc_hh = pow2_scale(lw.w_hh, sl.inv_hh), sc_hr = pow2_scale(lw.w_hr, sl.inv_hr);
+            std::vector<__half> wg((size_t)GC * 128 * D), wp((size_t)RS * 64 * H);
+            for (int c = 0; c < GC; c++)
+                for (int g4 = 0; g4 < 4; g4++)
+                    for (int u = 0; u < scan::UNITS; u++) {
+                        const float* src = lw.w_hh.data() + ((size_t)g4 * H + (size_t)c * scan::UNITS + u) * D;
+                        __half* hi = wg.data() + ((size_t)c * 128 + g4 * 16 + u) * D;
+                        __half* lo = wg.data() + ((size_t)c * 128 + 64 + g4 * 16 + u) * D;
+                        for (int k = 0; k < D; k++) { float x = src[k] * sc_hh; __half hh = __float2half_rn(x); hi[k] = hh; lo[k] = __float2half_rn(x - __half2float(hh)); }
+                    }
+            for (int r = 0; r < RS; r++)
+                for (int i = 0; i < scan::PROWS; i++) {
+                    const float* src = lw.w_hr.data() + ((size_t)r * scan::PROWS + i) * H;
+                    __half* hi = wp.data() + ((size_t)r * 64 + i) * H;
+                    __half* lo = wp.data() + ((size_t)r * 64 + 32 + i) * H;
+                    for (int k = 0; k < H; k++) { float x = src[k] * sc_hr; __half hh = __float2half_rn(x); hi[k] = hh; lo[k] = __float2half_rn(x - __half2float(hh)); }
+                }
+            sl.wg = upload(wg); sl.wp = upload(wp);
+            sl.mapWg = make_map_2d(sl.wg, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 128, (uint64_t)D, 64, 128, true);
+            sl.mapWp = make_map_2d(sl.wp, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)RS * 64, (uint64_t)H, 64, 64, true);
+            slayers.push_back(sl);
+        }
+        CK(cudaMalloc(&sx_h_hi, sizeof(__half) * 64 * (size_t)D)); CK(cudaMalloc(&sx_h_lo, sizeof(__half) * 64 * (size_t)D));
+        CK(cudaMalloc(&sx_m_hi, sizeof(__half) * 64 * (size_t)H)); CK(cudaMalloc(&sx_m_lo, sizeof(__half) * 64 * (size_t)H));
+        CK(cudaMemset(sx_m_hi, 0, sizeof(__half) * 64 * (size_t)H)); CK(cudaMemset(sx_m_lo, 0, sizeof(__half) * 64 * (size_t)H));
+        CK(cudaMalloc(&scan_counters, 2 * sizeof(unsigned)));
+        owned.push_back(sx_h_hi); owned.push_back(sx_h_lo); owned.push_back(sx_m_hi); owned.push_back(sx_m_lo); owned.push_back(scan_counters);
+    }
+
+    // one layer, steps [t0, t0+tc) of this pass: the recurrent scan on tensor cores, 64 sessions at a time
+    void scan_layer_tc(int l, const float* G, float* Hout, float* hw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
+        const int D = d.D, H = d.H;
+        ScanLayer& sl = slayers[(size_t)l];
+        for (int g0 = 0; g0 < B; g0 += 64) {
+            const int Bg = std::min(64, B - g0), Bp = (Bg + 15) & ~15;
+            scan::ScanArgs a{};
+            a.T = tc; a.t0 = t0; a.B = Bg; a.Bp = Bp; a.Bs = B; a.g0 = g0; a.D = D; a.H = H;
+            a.GC = H / scan::UNITS; a.RS = D / scan::PROWS; a.BSP = Bp / 16; a.Np = 16;
+            a.inv_scale_hh = sl.inv_hh; a.inv_scale_hr = sl.inv_hr;
+            a.nsteps = d_nsteps + g0; a.c_state = cw + (size_t)g0 * H; a.h_state = hw + (size_t)g0 * D;
+            a.h_hi = sx_h_hi; a.h_lo = sx_h_lo; a.m_hi = sx_m_hi; a.m_lo = sx_m_lo;
+            a.Hout = Hout + (size_t)g0 * D; a.counters = scan_counters;
+            scan::scan_prepare_kernel<<<32, 256, 0, st>>>(a.h_state, sx_h_hi, sx_h_lo, Bg, Bp, D); launch_check();
+            CK(cudaMemsetAsync(scan_counters, 0, 2 * sizeof(unsigned), st));
+            CUtensorMap mHh = make_map_2d(sx_h_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)D, 64, (uint32_t)Bp, true);
+            CUtensorMap mHl = make_map_2d(sx_h_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)D, 64, (uint32_t)Bp, true);
+            CUtensorMap mMh = make_map_2d(sx_m_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)H, 64, 16, true);
+            CUtensorMap mMl = make_map_2d(sx_m_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)H, 64, 16, true);
+            CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, 16, (uint32_t)Bp, false);
+            void* args[] = { &sl.mapWg, &sl.mapWp, &mHh, &mHl, &mMh, &mMl, &mG, &a };
+            const unsigned grid = (unsigned)(a.GC + a.RS * a.BSP);
+            CK(cudaLaunchCooperativeKernel((const void*)scan::lstm_scan_tc_kernel, dim3(grid), dim3(scan::THREADS), args, scan_smem, st));
+            launch_check();
+        }
     }
 
     void set_gemm_attrs() {
@@ -624,7 +732,8 @@ public:
                     float* hw = Hw + (size_t)l * B * D;
                     float* cw = Cw + (size_t)l * B * H;
                     span_begin(1);
-                    for (int t = 0; t < tc; t++) {
+                    if (npass && scan_tc) scan_layer_tc(l, G, Hout, hw, cw, d_nsteps, t0, tc, B);
+                    else for (int t = 0; t < tc; t++) {
                         k::lstm_gates_kernel<<<dim3((unsigned)(H / 16), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
                             G + (size_t)t * B * 4 * H, hw, w.w_hh, cw, Ms, d_nsteps, t0 + t, B, D, H);
                         launch_check();
