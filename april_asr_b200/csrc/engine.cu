@@ -158,6 +158,10 @@ public:
     k::FbankParams fp{};
     k::ConvParams cp{};
     float* dout_blank = nullptr;
+    float* dtab = nullptr;            // decoder output table [V][V][J] (fast greedy path)
+    bool fast_greedy = false;
+    int gr_R = 0;
+    size_t gr_smem = 0;
     int frame_N = 0, frame_shift = 0;
 
     // per-slot state
@@ -300,8 +304,29 @@ public:
         k::decoder_kernel<<<1, 256, (size_t)(d.E + d.J) * sizeof(float), st>>>(jp, prm.blank_id, prm.blank_id, dout_blank);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
+        init_fast_greedy();
         grow_slots(64);
         return true;
+    }
+
+    // cluster greedy kernel prerequisites: joiner rows fit 8 CTAs' shared memory, decoder table fits in HBM budget
+    void init_fast_greedy() {
+        const int V = d.V, J = d.J;
+        gr_R = (V + k::GC_CLUSTER - 1) / k::GC_CLUSTER;
+        gr_smem = sizeof(float) * ((size_t)gr_R * J + ((gr_R + 3) & ~3) + (size_t)k::GC_MAX_S * J + (size_t)k::GC_MAX_S * gr_R) + sizeof(k::GreedyPartial) * 2 * k::GC_CLUSTER * k::GC_MAX_S + 64;
+        const size_t tab_bytes = sizeof(float) * (size_t)V * V * J;
+        if (J % 32 != 0 || J / 32 > k::GC_MAX_JPL || gr_smem > 200 * 1024 || tab_bytes > ((size_t)3 << 30) || getenv("APRIL_B200_SLOW_GREEDY")) return;
+        CK(cudaMalloc(&dtab, tab_bytes));
+        float* Y = nullptr;
+        CK(cudaMalloc(&Y, sizeof(float) * (size_t)V * d.E));
+        for (int c0 = 0; c0 < V; c0++) {
+            k::decoder_table_y_kernel<<<V, 128, 0, st>>>(jp, c0, Y);
+            gemm_launch(k::EPI_BIAS, Y, jp.dec_w, jp.dec_b, nullptr, dtab + (size_t)c0 * V * J, V, J, d.E);
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(Y));
+        CK(cudaFuncSetAttribute(k::greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gr_smem));
+        fast_greedy = true;
     }
 
     size_t conv_smem() const {
@@ -312,7 +337,7 @@ public:
         cudaSetDevice(dev);
         if (st) cudaStreamSynchronize(st);
         for (void* p : owned) cudaFree(p);
-        cudaFree(dout_blank); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
+        cudaFree(dout_blank); cudaFree(dtab); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -759,8 +784,16 @@ public:
                 if (npass == 0) gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
                 else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
-                k::greedy_kernel<<<B, 256, greedy_smem, st>>>(jp, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate, dout_store, dout_blank,
-                                                             b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc);
+                if (fast_greedy) {
+                    const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
+                    const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));
+                    const int ncl = (B + S - 1) / S;
+                    k::greedy_cluster_kernel<<<ncl * k::GC_CLUSTER, 256, gr_smem, st>>>(jp, dtab, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate,
+                                                                                        b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc, S, gr_R);
+                } else {
+                    k::greedy_kernel<<<B, 256, greedy_smem, st>>>(jp, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate, dout_store, dout_blank,
+                                                                 b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc);
+                }
                 launch_check();
                 if (want_tap) { CK(cudaMemcpyAsync(p_eo.as<float>() + (size_t)t0 * B * J, EO, sizeof(float) * (size_t)M * J, cudaMemcpyDeviceToHost, st)); stat.d2h_bytes += sizeof(float) * (size_t)M * J; }
             }

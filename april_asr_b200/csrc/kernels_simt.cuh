@@ -609,5 +609,180 @@ greedy_kernel(JoinerParams P, const float* __restrict__ enc_out /*[T*B, J] time-
     for (int j = threadIdx.x; j < P.J; j += blockDim.x) dout_store[(size_t)sl * P.J + j] = d_s[j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// J1 + G1, cluster version: a thread-block cluster of 8 CTAs keeps the joiner output matrix
+// resident in (distributed) shared memory — CTA r owns vocabulary rows [r*R, r*R+R) in fp32 — and
+// walks S sessions step-synchronously. Per joiner pass every CTA forms z = tanh(e + d) for its
+// sessions, multiplies its rows, publishes (best non-blank value, index, blank logit) to all 8
+// CTAs over DSMEM, and after one cluster barrier every CTA evaluates the same greedy rule on the
+// same 8 partials (replicated, deterministic state), so no second exchange is needed.
+// The stateless decoder (D1) is a table lookup: dtab[(c0 * V + c1) * J + j], built once per model
+// from the same arithmetic as decoder_eval (the decoder output is a pure function of the two
+// context tokens: SURVEY.md §8a D1).
+// ------------------------------------------------------------------------------------------------
+constexpr int GC_CLUSTER = 8;
+constexpr int GC_MAX_S = 8;          // sessions per cluster
+constexpr int GC_MAX_JPL = 16;       // J / 32
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_store_f32(const void* local_smem_ptr, uint32_t rank, float v) {
+    uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+
+struct GreedyPartial { float best_val; float best_idx; float blank_val; float has_blank; };
+
+__global__ void __cluster_dims__(GC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
+greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const float* __restrict__ enc_out /*[T*B, J] chunk, time-major*/,
+                      const int* __restrict__ nsteps, const int* __restrict__ slot, const int* __restrict__ flush_flag, int B, int Tcap, int t_base,
+                      int stride_ms, GreedyState* __restrict__ gstate, DecisionRecord* __restrict__ rec, int* __restrict__ npass,
+                      float* __restrict__ tap_logits, int last_chunk, int chunk_T, int S, int R) {
+    extern __shared__ float smem_f[];
+    const int J = P.J, V = P.V;
+    const uint32_t rank = cluster_rank();
+    const int cid = blockIdx.x / GC_CLUSTER;
+    const int s0 = cid * S;
+    const int ns = min(S, B - s0);                         // sessions of this cluster (cluster-uniform)
+    float* Ws = smem_f;                                    // [R][J]
+    float* bs = Ws + (size_t)R * J;                        // [R]
+    float* zs = bs + ((R + 3) & ~3);                       // [S][J]
+    GreedyPartial* inbox = reinterpret_cast<GreedyPartial*>(zs + (size_t)S * J);   // [2][8][S]
+    float* logit_s = reinterpret_cast<float*>(inbox + 2 * GC_CLUSTER * S);         // [S][R] scratch
+    __shared__ GreedyState st[GC_MAX_S];
+    __shared__ int s_done[GC_MAX_S], s_np[GC_MAX_S], s_live[GC_MAX_S];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int row0 = (int)rank * R;
+    const int jpl = J / 32;
+
+    for (int i = threadIdx.x; i < R * J; i += blockDim.x) { int r = row0 + i / J; Ws[i] = r < V ? P.join_w[(size_t)r * J + (i % J)] : 0.f; }
+    for (int i = threadIdx.x; i < R; i += blockDim.x) bs[i] = row0 + i < V ? P.join_b[row0 + i] : 0.f;
+    if (threadIdx.x < ns) st[threadIdx.x] = gstate[slot[s0 + threadIdx.x]];
+    __syncthreads();
+    if (ns <= 0) { cluster_sync_all(); return; }            // (never: the host launches only populated clusters)
+
+    int t_end = 0;
+    for (int s = 0; s < ns; s++) t_end = max(t_end, min(nsteps[s0 + s], t_base + chunk_T));
+    int parity = 0;
+    for (int t = t_base; t < t_end; t++) {
+        if (threadIdx.x < ns) {
+            const int s = threadIdx.x;
+            const bool act = t < nsteps[s0 + s];
+            s_done[s] = act ? 0 : 1; s_np[s] = 0;
+            if (act) st[s].current_ms += stride_ms;                           // april_session.c:442-443
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 3; pass++) {
+            // z = tanh(e + d) for live sessions
+            for (int i = threadIdx.x; i < ns * J; i += blockDim.x) {
+                const int s = i / J, j = i % J;
+                if (s_done[s]) continue;
+                const float e = enc_out[((size_t)(t - t_base) * B + s0 + s) * J + j];
+                const float dv = dtab[((size_t)st[s].ctx0 * V + st[s].ctx1) * J + j];
+                zs[s * J + j] = tanhf(e + dv);
+            }
+            if (threadIdx.x < ns) s_live[threadIdx.x] = !s_done[threadIdx.x];
+            __syncthreads();
+            // my rows x live sessions
+            float zr[GC_MAX_S][GC_MAX_JPL];
+#pragma unroll
+            for (int s = 0; s < GC_MAX_S; s++)
+#pragma unroll
+                for (int i = 0; i < GC_MAX_JPL; i++) zr[s][i] = (s < ns && i < jpl && s_live[s]) ? zs[s * J + lane + 32 * i] : 0.f;
+            for (int r = warp; r < R; r += nw) {
+                float acc[GC_MAX_S];
+#pragma unroll
+                for (int s = 0; s < GC_MAX_S; s++) acc[s] = 0.f;
+                const float* w = Ws + (size_t)r * J;
+#pragma unroll
+                for (int i = 0; i < GC_MAX_JPL; i++) {
+                    if (i >= jpl) break;
+                    const float wv = w[lane + 32 * i];
+#pragma unroll
+                    for (int s = 0; s < GC_MAX_S; s++) acc[s] = fmaf(zr[s][i], wv, acc[s]);
+                }
+#pragma unroll
+                for (int s = 0; s < GC_MAX_S; s++) {
+                    if (s >= ns) break;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+                    if (lane == 0) logit_s[s * R + r] = acc[s] + bs[r];
+                }
+            }
+            __syncthreads();
+            // local arg-max per session (ascending row order => lowest index on ties), published to all 8 CTAs
+            if (threadIdx.x < ns && s_live[threadIdx.x]) {
+                const int s = threadIdx.x;
+                float bv = (float)(-9999999999.0); int bi = -1; float blank_v = 0.f; float has_blank = 0.f;
+                float* tl = tap_logits ? tap_logits + (((size_t)(s0 + s) * Tcap + t) * 3 + pass) * V : nullptr;
+                for (int r = 0; r < R; r++) {
+                    const int v = row0 + r;
+                    if (v >= V) break;
+                    const float x = logit_s[s * R + r];
+                    if (tl) tl[v] = x;
+                    if (v == P.blank) { blank_v = x; has_blank = 1.f; }
+                    else if (x > bv) { bv = x; bi = v; }
+                }
+                GreedyPartial* slot_local = &inbox[(parity * GC_CLUSTER + rank) * S + s];
+                for (uint32_t dst = 0; dst < GC_CLUSTER; dst++) {
+                    dsmem_store_f32(&slot_local->best_val, dst, bv);
+                    dsmem_store_f32(&slot_local->best_idx, dst, (float)bi);
+                    dsmem_store_f32(&slot_local->blank_val, dst, blank_v);
+                    dsmem_store_f32(&slot_local->has_blank, dst, has_blank);
+                }
+            }
+            cluster_sync_all();
+            if (threadIdx.x < ns && s_live[threadIdx.x]) {
+                const int s = threadIdx.x;
+                float mv = (float)(-9999999999.0); int mi = -1; float blank_v = 0.f;
+                for (int c = 0; c < GC_CLUSTER; c++) {                        // rank order == ascending vocabulary order
+                    const GreedyPartial& p = inbox[(parity * GC_CLUSTER + c) * S + s];
+                    if (p.has_blank != 0.f) blank_v = p.blank_val;
+                    if ((int)p.best_idx >= 0 && p.best_val > mv) { mv = p.best_val; mi = (int)p.best_idx; }
+                }
+                bool ctx_changed;
+                const bool is_blank = greedy_decide(st[s], P.vflags, P.blank, pass == 0 ? 1.0f : 0.0f, mi, mv, blank_v, ctx_changed);
+                if (rank == 0) {
+                    DecisionRecord r; r.max_idx = mi; r.is_blank = is_blank ? 1 : 0; r.max_val = mv; r.blank_val = blank_v;
+                    rec[((size_t)(s0 + s) * Tcap + t) * 3 + pass] = r;
+                }
+                s_np[s] = pass + 1;
+                if (is_blank) s_done[s] = 1;
+            }
+            parity ^= 1;
+            __syncthreads();
+            bool all_done = true;
+            for (int s = 0; s < ns; s++) all_done &= (s_done[s] != 0);
+            if (all_done) break;
+        }
+        if (rank == 0 && threadIdx.x < ns && t < nsteps[s0 + threadIdx.x]) npass[(size_t)(s0 + threadIdx.x) * Tcap + t] = s_np[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x < ns) {
+        const int s = threadIdx.x;
+        if (last_chunk && flush_flag[s0 + s]) {                               // _aas_flush tail, april_session.c:561-563
+            st[s].head = 0;
+            if (st[s].ctx0 != P.blank) { st[s].ctx0 = P.blank; st[s].ctx1 = P.blank; }
+        }
+        if (rank == 0) gstate[slot[s0 + s]] = st[s];
+    }
+    cluster_sync_all();                                                       // no CTA may exit while peers can still write its inbox
+}
+
+// decoder table rows for context (c0, *): Y[c1][e] = relu(emb[c0][e] k[e][0] + emb[c1][e] k[e][1])
+__global__ void decoder_table_y_kernel(JoinerParams P, int c0, float* __restrict__ Y) {
+    const int c1 = blockIdx.x;
+    for (int e = threadIdx.x; e < P.E; e += blockDim.x) {
+        float s = 0.f;
+        s = fmaf(P.emb[(size_t)c0 * P.E + e], P.dec_conv[e * 2 + 0], s);
+        s = fmaf(P.emb[(size_t)c1 * P.E + e], P.dec_conv[e * 2 + 1], s);
+        Y[(size_t)c1 * P.E + e] = fmaxf(s, 0.f);
+    }
+}
+
 }  // namespace k
 }  // namespace april
