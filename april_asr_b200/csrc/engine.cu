@@ -66,6 +66,20 @@ static CUtensorMap make_map_2d(const void* ptr, CUtensorMapDataType dt, size_t e
     return m;
 }
 
+// 3-D view of a row-major fp16 matrix [rows, cols]: {64-wide k-block element, row, k-block index}; one box = box_kb k-blocks of
+// box_rows rows, each k-block landing as a [box_rows x 128 B] 128B-swizzled tile (what UMMA K-major descriptors expect)
+static CUtensorMap make_map_kblocks(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_kb) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = { 64, rows, cols / 64 };
+    cuuint64_t strides[2] = { cols * sizeof(__half), 64 * sizeof(__half) };
+    cuuint32_t box[3] = { 64, box_rows, box_kb };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (3-D) failed: %d\n", (int)r); abort(); }
+    return m;
+}
+
 struct TcWeight {                   // fp16 (hi, lo) copies of a [N, K] weight, pre-scaled by a power of two
     __half *hi = nullptr, *lo = nullptr;
     float inv_scale = 1.f;
@@ -153,6 +167,8 @@ public:
     __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
     unsigned* scan_counters = nullptr;
     size_t scan_smem = 0;
+    int scan_kbg = 1;
+    DevBuf b_trace;
     DevBuf b_xe_h, b_xe_l, b_x_h, b_x_l, b_x1_h, b_x1_l, b_f1_h, b_f1_l;
     k::JoinerParams jp{};
     k::FbankParams fp{};
@@ -438,8 +454,16 @@ public:
         scan_tc = (D % 64 == 0) && (H % 64 == 0) && (H % scan::UNITS == 0) && (D % scan::PROWS == 0) && (GC + RS * 4 <= num_sms) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
         if (!scan_tc) return;
         const size_t wbytes = std::max<size_t>((size_t)(D / 64) * 16384, (size_t)(H / 64) * 8192);
-        scan_smem = 1024 + wbytes + std::max<size_t>((size_t)scan::NSTAGE * 64 * 128, (size_t)128 * 65 * 4) + 1024 + 2 * (size_t)64 * 16 * 16 + (size_t)64 * scan::UNITS * 4 + 512;
-        if (scan_smem > 227 * 1024) { scan_tc = false; return; }
+        // shared-memory plan (per role): resident weights + activation buffer + (gate: G buffer, c state) + barriers
+        const int KBW = D / 64;
+        scan_kbg = std::max(1, KBW / 4);
+        { int copies = 2 * KBW / scan_kbg; if (KBW % scan_kbg || (copies > scan::GSTAGES && copies % scan::GSTAGES)) scan_kbg = KBW; }
+        const size_t act_gate = std::max<size_t>((size_t)scan::GSTAGES * scan_kbg * 64 * 128, 33280);
+        const size_t act_proj = std::max<size_t>((size_t)2 * (H / 64) * 16 * 128, 33280);
+        const size_t smem_gate = 1024 + (size_t)KBW * 16384 + act_gate + 1024 + (size_t)64 * 256 + (size_t)64 * scan::UNITS * 4 + 256;
+        const size_t smem_proj = 1024 + (size_t)(H / 64) * 8192 + act_proj + 1024 + 256;
+        scan_smem = std::max(smem_gate, smem_proj);
+        if (scan_smem > 227 * 1024 || H / 64 > 256) { scan_tc = false; return; }
         CK(cudaFuncSetAttribute(scan::lstm_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
         for (auto& lw : w.layers) {
             ScanLayer sl;
@@ -472,6 +496,29 @@ public:
         owned.push_back(sx_h_hi); owned.push_back(sx_h_lo); owned.push_back(sx_m_hi); owned.push_back(sx_m_lo); owned.push_back(scan_counters);
     }
 
+    void dump_trace(int grid, int T, int GC) {
+        std::vector<unsigned long long> h((size_t)grid * T * 8);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(h.data(), b_trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        auto at = [&](int cta, int t, int k) { return (double)h[((size_t)cta * T + t) * 8 + k]; };
+        // averages over steps 8..T-8 for gate CTA 0 and projection CTA GC; times relative to the gate CTA's stamp 0 of the same step
+        double acc_g[8] = {0}, acc_p[8] = {0}; int n = 0;
+        double step = 0;
+        for (int t = 8; t < T - 8; t++, n++) {
+            double t0g = at(0, t, 0);
+            for (int k2 = 0; k2 < 8; k2++) { acc_g[k2] += at(0, t, k2) - t0g; acc_p[k2] += at(GC, t, k2) - t0g; }
+            step += at(0, t + 1, 0) - t0g;
+        }
+        fprintf(stderr, "scan trace (ns, rel. to gate stamp0, avg of %d steps; step = %.0f ns)\n  gate: ", n, step / n);
+        for (int k2 = 0; k2 < 8; k2++) fprintf(stderr, "%d:%.0f ", k2, acc_g[k2] / n);
+        fprintf(stderr, "\n  proj: ");
+        for (int k2 = 0; k2 < 8; k2++) fprintf(stderr, "%d:%.0f ", k2, acc_p[k2] / n);
+        // spread across CTAs of stamp 7 (release) at one step
+        double mn = 1e30, mx = 0; for (int c = 0; c < GC; c++) { double v = at(c, T / 2, 7) - at(0, T / 2, 0); mn = std::min(mn, v); mx = std::max(mx, v); }
+        double mn2 = 1e30, mx2 = 0; for (int c = GC; c < grid; c++) { double v = at(c, T / 2, 7) - at(0, T / 2, 0); mn2 = std::min(mn2, v); mx2 = std::max(mx2, v); }
+        fprintf(stderr, "\n  gate release spread [%.0f, %.0f]  proj release spread [%.0f, %.0f]\n", mn, mx, mn2, mx2);
+    }
+
     // one layer, steps [t0, t0+tc) of this pass: the recurrent scan on tensor cores, 64 sessions at a time
     void scan_layer_tc(int l, const float* G, float* Hout, float* hw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int D = d.D, H = d.H;
@@ -481,21 +528,27 @@ public:
             scan::ScanArgs a{};
             a.T = tc; a.t0 = t0; a.B = Bg; a.Bp = Bp; a.Bs = B; a.g0 = g0; a.D = D; a.H = H;
             a.GC = H / scan::UNITS; a.RS = D / scan::PROWS; a.BSP = Bp / 16; a.Np = 16;
+            a.KBG = scan_kbg;
             a.inv_scale_hh = sl.inv_hh; a.inv_scale_hr = sl.inv_hr;
             a.nsteps = d_nsteps + g0; a.c_state = cw + (size_t)g0 * H; a.h_state = hw + (size_t)g0 * D;
             a.h_hi = sx_h_hi; a.h_lo = sx_h_lo; a.m_hi = sx_m_hi; a.m_lo = sx_m_lo;
             a.Hout = Hout + (size_t)g0 * D; a.counters = scan_counters;
+            static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
+            const unsigned grid_n = (unsigned)(H / scan::UNITS + (D / scan::PROWS) * (Bp / 16));
+            const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
+            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)grid_n * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)grid_n * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
             scan::scan_prepare_kernel<<<32, 256, 0, st>>>(a.h_state, sx_h_hi, sx_h_lo, Bg, Bp, D); launch_check();
             CK(cudaMemsetAsync(scan_counters, 0, 2 * sizeof(unsigned), st));
-            CUtensorMap mHh = make_map_2d(sx_h_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)D, 64, (uint32_t)Bp, true);
-            CUtensorMap mHl = make_map_2d(sx_h_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)D, 64, (uint32_t)Bp, true);
-            CUtensorMap mMh = make_map_2d(sx_m_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)H, 64, 16, true);
-            CUtensorMap mMl = make_map_2d(sx_m_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)Bp, (uint64_t)H, 64, 16, true);
+            CUtensorMap mHh = make_map_kblocks(sx_h_hi, (uint64_t)Bp, (uint64_t)D, (uint32_t)Bp, (uint32_t)scan_kbg);
+            CUtensorMap mHl = make_map_kblocks(sx_h_lo, (uint64_t)Bp, (uint64_t)D, (uint32_t)Bp, (uint32_t)scan_kbg);
+            CUtensorMap mMh = make_map_kblocks(sx_m_hi, (uint64_t)Bp, (uint64_t)H, 16, (uint32_t)(H / 64));
+            CUtensorMap mMl = make_map_kblocks(sx_m_lo, (uint64_t)Bp, (uint64_t)H, 16, (uint32_t)(H / 64));
             CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, 16, (uint32_t)Bp, false);
             void* args[] = { &sl.mapWg, &sl.mapWp, &mHh, &mHl, &mMh, &mMl, &mG, &a };
             const unsigned grid = (unsigned)(a.GC + a.RS * a.BSP);
             CK(cudaLaunchCooperativeKernel((const void*)scan::lstm_scan_tc_kernel, dim3(grid), dim3(scan::THREADS), args, scan_smem, st));
             launch_check();
+            if (do_trace) dump_trace((int)grid, tc, a.GC);
         }
     }
 
