@@ -329,9 +329,9 @@ public:
     void init_fast_greedy() {
         const int V = d.V, J = d.J;
         gr_R = (V + k::GC_CLUSTER - 1) / k::GC_CLUSTER;
-        gr_smem = sizeof(float) * ((size_t)gr_R * J + ((gr_R + 3) & ~3) + (size_t)k::GC_MAX_S * J + (size_t)k::GC_MAX_S * gr_R) + sizeof(k::GreedyPartial) * 2 * k::GC_CLUSTER * k::GC_MAX_S + 64;
+        gr_smem = sizeof(float) * ((size_t)4 * k::GC_MAX_S * J + (size_t)k::GC_MAX_S * ((gr_R + 3) & ~3)) + sizeof(k::GreedyPartial) * 2 * k::GC_CLUSTER * k::GC_MAX_S + (size_t)V + 64;
         const size_t tab_bytes = sizeof(float) * (size_t)V * V * J;
-        if (J % 32 != 0 || J / 32 > k::GC_MAX_JPL || gr_smem > 200 * 1024 || tab_bytes > ((size_t)3 << 30) || getenv("APRIL_B200_SLOW_GREEDY")) return;
+        if (J % 32 != 0 || J / 32 > k::GC_MAX_JPL || J > 512 || gr_R > 8 * k::GC_RPW || gr_smem > 200 * 1024 || tab_bytes > ((size_t)3 << 30) || getenv("APRIL_B200_SLOW_GREEDY")) return;
         CK(cudaMalloc(&dtab, tab_bytes));
         float* Y = nullptr;
         CK(cudaMalloc(&Y, sizeof(float) * (size_t)V * d.E));

@@ -637,6 +637,26 @@ __device__ __forceinline__ void dsmem_store_f32(const void* local_smem_ptr, uint
 
 struct GreedyPartial { float best_val; float best_idx; float blank_val; float has_blank; };
 
+constexpr int GC_RPW = 8;            // vocabulary rows per warp (8 warps -> up to 64 rows per CTA, 512 per cluster)
+constexpr int GC_SG = 4;             // sessions processed per register round
+
+// sum over the 32 lanes of 32 per-lane values; lane l ends up with the total of value index l
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i < n / 2) {
+                const float send = up ? v[i] : v[i + n / 2];
+                const float keep = up ? v[i + n / 2] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    return v[0];
+}
+
 __global__ void __cluster_dims__(GC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
 greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const float* __restrict__ enc_out /*[T*B, J] chunk, time-major*/,
                       const int* __restrict__ nsteps, const int* __restrict__ slot, const int* __restrict__ flush_flag, int B, int Tcap, int t_base,
@@ -648,95 +668,134 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
     const int cid = blockIdx.x / GC_CLUSTER;
     const int s0 = cid * S;
     const int ns = min(S, B - s0);                         // sessions of this cluster (cluster-uniform)
-    float* Ws = smem_f;                                    // [R][J]
-    float* bs = Ws + (size_t)R * J;                        // [R]
-    float* zs = bs + ((R + 3) & ~3);                       // [S][J]
-    GreedyPartial* inbox = reinterpret_cast<GreedyPartial*>(zs + (size_t)S * J);   // [2][8][S]
-    float* logit_s = reinterpret_cast<float*>(inbox + 2 * GC_CLUSTER * S);         // [S][R] scratch
+    const int Rp = (R + 3) & ~3;
+    float* es = smem_f;                                    // [2][S][J] encoder rows: current step / prefetched next step
+    float* ds = es + (size_t)2 * S * J;                    // [S][J] decoder rows of the current contexts
+    float* zs = ds + (size_t)S * J;                        // [S][J] tanh(e + d)
+    float* logit_s = zs + (size_t)S * J;                   // [S][Rp]
+    GreedyPartial* inbox = reinterpret_cast<GreedyPartial*>(logit_s + (size_t)S * Rp);   // [2][8][S]
+    uint8_t* vf_s = reinterpret_cast<uint8_t*>(inbox + 2 * GC_CLUSTER * S);               // [V]
     __shared__ GreedyState st[GC_MAX_S];
-    __shared__ int s_done[GC_MAX_S], s_np[GC_MAX_S], s_live[GC_MAX_S];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __shared__ int s_done[GC_MAX_S], s_np[GC_MAX_S], s_newctx[GC_MAX_S], s_n[GC_MAX_S];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = (int)rank * R;
     const int jpl = J / 32;
 
-    for (int i = threadIdx.x; i < R * J; i += blockDim.x) { int r = row0 + i / J; Ws[i] = r < V ? P.join_w[(size_t)r * J + (i % J)] : 0.f; }
-    for (int i = threadIdx.x; i < R; i += blockDim.x) bs[i] = row0 + i < V ? P.join_b[row0 + i] : 0.f;
-    if (threadIdx.x < ns) st[threadIdx.x] = gstate[slot[s0 + threadIdx.x]];
+    // this warp's rows of the joiner matrix live in registers for the whole launch: w[r][i] = W[row0 + warp*8 + r][lane + 32 i]
+    float w[GC_RPW][GC_MAX_JPL];
+    float bias_r = 0.f;                                    // bias of the row this lane reports after the reduce-scatter (row lane/4)
+#pragma unroll
+    for (int r = 0; r < GC_RPW; r++) {
+        const int lr = warp * GC_RPW + r, v = row0 + lr;
+#pragma unroll
+        for (int i = 0; i < GC_MAX_JPL; i++) w[r][i] = (lr < R && v < V && i < jpl) ? P.join_w[(size_t)v * J + lane + 32 * i] : 0.f;
+    }
+    {
+        const int lr = warp * GC_RPW + lane / GC_SG, v = row0 + lr;
+        bias_r = (lr < R && v < V) ? P.join_b[v] : 0.f;
+    }
+    for (int i = threadIdx.x; i < V; i += blockDim.x) vf_s[i] = P.vflags[i];
+    if (threadIdx.x < ns) { st[threadIdx.x] = gstate[slot[s0 + threadIdx.x]]; s_newctx[threadIdx.x] = 1; s_n[threadIdx.x] = nsteps[s0 + threadIdx.x]; }
     __syncthreads();
     if (ns <= 0) { cluster_sync_all(); return; }            // (never: the host launches only populated clusters)
 
     int t_end = 0;
-    for (int s = 0; s < ns; s++) t_end = max(t_end, min(nsteps[s0 + s], t_base + chunk_T));
+    for (int s = 0; s < ns; s++) t_end = max(t_end, min(s_n[s], t_base + chunk_T));
+    // encoder rows of the first step
+    for (int s = 0; s < ns; s++)
+        if (t_base < s_n[s]) for (int j = threadIdx.x; j < J; j += blockDim.x) es[(size_t)s * J + j] = enc_out[((size_t)0 * B + s0 + s) * J + j];
     int parity = 0;
     for (int t = t_base; t < t_end; t++) {
+        const float* e_cur = es + (size_t)((t - t_base) & 1) * S * J;
+        float* e_nxt = es + (size_t)((t - t_base + 1) & 1) * S * J;
         if (threadIdx.x < ns) {
             const int s = threadIdx.x;
-            const bool act = t < nsteps[s0 + s];
+            const bool act = t < s_n[s];
             s_done[s] = act ? 0 : 1; s_np[s] = 0;
             if (act) st[s].current_ms += stride_ms;                           // april_session.c:442-443
         }
         __syncthreads();
         for (int pass = 0; pass < 3; pass++) {
-            // z = tanh(e + d) for live sessions
-            for (int i = threadIdx.x; i < ns * J; i += blockDim.x) {
-                const int s = i / J, j = i % J;
+            // --- A: decoder rows for changed contexts (table lookup = aas_run_decoder), z = tanh(e + d); prefetch next step's e
+            float e_pf[GC_MAX_S][2];
+            const bool do_pf = pass == 0 && t + 1 < t_end;
+            for (int s = 0; s < ns; s++) {
+                if (do_pf && t + 1 < s_n[s]) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) { const int j = threadIdx.x + u * 256; e_pf[s][u] = j < J ? enc_out[((size_t)(t + 1 - t_base) * B + s0 + s) * J + j] : 0.f; }
+                }
                 if (s_done[s]) continue;
-                const float e = enc_out[((size_t)(t - t_base) * B + s0 + s) * J + j];
-                const float dv = dtab[((size_t)st[s].ctx0 * V + st[s].ctx1) * J + j];
-                zs[s * J + j] = tanhf(e + dv);
+                const bool nc = s_newctx[s] != 0;
+                const float* drow = dtab + ((size_t)st[s].ctx0 * V + st[s].ctx1) * J;
+                for (int j = threadIdx.x; j < J; j += blockDim.x) {
+                    float dv;
+                    if (nc) { dv = drow[j]; ds[(size_t)s * J + j] = dv; } else dv = ds[(size_t)s * J + j];
+                    zs[(size_t)s * J + j] = tanhf(e_cur[(size_t)s * J + j] + dv);
+                }
             }
-            if (threadIdx.x < ns) s_live[threadIdx.x] = !s_done[threadIdx.x];
             __syncthreads();
-            // my rows x live sessions
-            float zr[GC_MAX_S][GC_MAX_JPL];
+            if (threadIdx.x < ns) s_newctx[threadIdx.x] = 0;
+            // --- B: logits of my rows: registers x shared z, 4 sessions per round
+            for (int sg = 0; sg < ns; sg += GC_SG) {
+                float acc[32];
 #pragma unroll
-            for (int s = 0; s < GC_MAX_S; s++)
-#pragma unroll
-                for (int i = 0; i < GC_MAX_JPL; i++) zr[s][i] = (s < ns && i < jpl && s_live[s]) ? zs[s * J + lane + 32 * i] : 0.f;
-            for (int r = warp; r < R; r += nw) {
-                float acc[GC_MAX_S];
-#pragma unroll
-                for (int s = 0; s < GC_MAX_S; s++) acc[s] = 0.f;
-                const float* w = Ws + (size_t)r * J;
+                for (int p = 0; p < 32; p++) acc[p] = 0.f;
 #pragma unroll
                 for (int i = 0; i < GC_MAX_JPL; i++) {
-                    if (i >= jpl) break;
-                    const float wv = w[lane + 32 * i];
+                    if (i < jpl) {
+                        float z[GC_SG];
 #pragma unroll
-                    for (int s = 0; s < GC_MAX_S; s++) acc[s] = fmaf(zr[s][i], wv, acc[s]);
+                        for (int q = 0; q < GC_SG; q++) z[q] = (sg + q < ns) ? zs[(sg + q) * J + lane + 32 * i] : 0.f;
+#pragma unroll
+                        for (int r = 0; r < GC_RPW; r++)
+#pragma unroll
+                            for (int q = 0; q < GC_SG; q++) acc[r * GC_SG + q] = fmaf(w[r][i], z[q], acc[r * GC_SG + q]);
+                    }
                 }
-#pragma unroll
-                for (int s = 0; s < GC_MAX_S; s++) {
-                    if (s >= ns) break;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
-                    if (lane == 0) logit_s[s * R + r] = acc[s] + bs[r];
-                }
+                const float tot = warp_reduce_scatter32(acc, lane);          // lane -> (row lane/4, session sg + lane%4)
+                const int lr = warp * GC_RPW + lane / GC_SG, sq = sg + lane % GC_SG;
+                if (lr < R && sq < ns) logit_s[sq * Rp + lr] = tot + bias_r;
             }
+            if (do_pf && J <= 512)
+                for (int s = 0; s < ns; s++) if (t + 1 < s_n[s]) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) { const int j = threadIdx.x + u * 256; if (j < J) e_nxt[(size_t)s * J + j] = e_pf[s][u]; }
+                }
             __syncthreads();
-            // local arg-max per session (ascending row order => lowest index on ties), published to all 8 CTAs
-            if (threadIdx.x < ns && s_live[threadIdx.x]) {
-                const int s = threadIdx.x;
-                float bv = (float)(-9999999999.0); int bi = -1; float blank_v = 0.f; float has_blank = 0.f;
+            // --- C: warp s = local arg-max of session s over my rows (ties -> lowest index), published to all 8 CTAs over DSMEM
+            if (warp < ns && !s_done[warp]) {
+                const int s = warp;
+                float bv = (float)(-9999999999.0); int bi = -1; float blank_v = 0.f; int has_blank = 0;
                 float* tl = tap_logits ? tap_logits + (((size_t)(s0 + s) * Tcap + t) * 3 + pass) * V : nullptr;
-                for (int r = 0; r < R; r++) {
+                const float* lg = logit_s + s * Rp;
+                for (int r = lane; r < R; r += 32) {
                     const int v = row0 + r;
                     if (v >= V) break;
-                    const float x = logit_s[s * R + r];
+                    const float x = lg[r];
                     if (tl) tl[v] = x;
-                    if (v == P.blank) { blank_v = x; has_blank = 1.f; }
+                    if (v == P.blank) { blank_v = x; has_blank = 1; }
                     else if (x > bv) { bv = x; bi = v; }
                 }
-                GreedyPartial* slot_local = &inbox[(parity * GC_CLUSTER + rank) * S + s];
-                for (uint32_t dst = 0; dst < GC_CLUSTER; dst++) {
-                    dsmem_store_f32(&slot_local->best_val, dst, bv);
-                    dsmem_store_f32(&slot_local->best_idx, dst, (float)bi);
-                    dsmem_store_f32(&slot_local->blank_val, dst, blank_v);
-                    dsmem_store_f32(&slot_local->has_blank, dst, has_blank);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const float ob = __shfl_xor_sync(0xffffffffu, blank_v, o);
+                    const int oh = __shfl_xor_sync(0xffffffffu, has_blank, o);
+                    if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+                    if (oh) { blank_v = ob; has_blank = 1; }
+                }
+                if (lane < GC_CLUSTER) {
+                    GreedyPartial* slot_local = &inbox[(parity * GC_CLUSTER + rank) * S + s];
+                    dsmem_store_f32(&slot_local->best_val, lane, bv);
+                    dsmem_store_f32(&slot_local->best_idx, lane, (float)bi);
+                    dsmem_store_f32(&slot_local->blank_val, lane, blank_v);
+                    dsmem_store_f32(&slot_local->has_blank, lane, has_blank ? 1.f : 0.f);
                 }
             }
             cluster_sync_all();
-            if (threadIdx.x < ns && s_live[threadIdx.x]) {
+            // --- D: every CTA evaluates the same rule on the same 8 partials (replicated state)
+            if (threadIdx.x < ns && !s_done[threadIdx.x]) {
                 const int s = threadIdx.x;
                 float mv = (float)(-9999999999.0); int mi = -1; float blank_v = 0.f;
                 for (int c = 0; c < GC_CLUSTER; c++) {                        // rank order == ascending vocabulary order
@@ -745,12 +804,13 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
                     if ((int)p.best_idx >= 0 && p.best_val > mv) { mv = p.best_val; mi = (int)p.best_idx; }
                 }
                 bool ctx_changed;
-                const bool is_blank = greedy_decide(st[s], P.vflags, P.blank, pass == 0 ? 1.0f : 0.0f, mi, mv, blank_v, ctx_changed);
+                const bool is_blank = greedy_decide(st[s], vf_s, P.blank, pass == 0 ? 1.0f : 0.0f, mi, mv, blank_v, ctx_changed);
                 if (rank == 0) {
                     DecisionRecord r; r.max_idx = mi; r.is_blank = is_blank ? 1 : 0; r.max_val = mv; r.blank_val = blank_v;
                     rec[((size_t)(s0 + s) * Tcap + t) * 3 + pass] = r;
                 }
                 s_np[s] = pass + 1;
+                if (ctx_changed) s_newctx[s] = 1;
                 if (is_blank) s_done[s] = 1;
             }
             parity ^= 1;
@@ -759,9 +819,9 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
             for (int s = 0; s < ns; s++) all_done &= (s_done[s] != 0);
             if (all_done) break;
         }
-        if (rank == 0 && threadIdx.x < ns && t < nsteps[s0 + threadIdx.x]) npass[(size_t)(s0 + threadIdx.x) * Tcap + t] = s_np[threadIdx.x];
-        __syncthreads();
+        if (rank == 0 && threadIdx.x < ns && t < s_n[threadIdx.x]) npass[(size_t)(s0 + threadIdx.x) * Tcap + t] = s_np[threadIdx.x];
     }
+    __syncthreads();
     if (threadIdx.x < ns) {
         const int s = threadIdx.x;
         if (last_chunk && flush_flag[s0 + s]) {                               // _aas_flush tail, april_session.c:561-563
