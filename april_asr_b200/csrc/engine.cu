@@ -80,6 +80,20 @@ static CUtensorMap make_map_kblocks(const void* ptr, uint64_t rows, uint64_t col
     return m;
 }
 
+// 4-D view of a stacked exchange buffer [2 (hi|lo)][rows][cols] fp16: {64-wide k-block element, row, hi|lo, k-block index}; one box =
+// box_kb k-blocks, each landing as a [2 * box_rows x 128 B] 128B-swizzled tile = UMMA B operand with N = 2 * box_rows
+static CUtensorMap make_map_kblocks_hl(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_kb) {
+    CUtensorMap m;
+    cuuint64_t dims[4] = { 64, rows, 2, cols / 64 };
+    cuuint64_t strides[3] = { cols * sizeof(__half), rows * cols * sizeof(__half), 64 * sizeof(__half) };
+    cuuint32_t box[4] = { 64, box_rows, 2, box_kb };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (4-D) failed: %d\n", (int)r); abort(); }
+    return m;
+}
+
 struct TcWeight {                   // fp16 (hi, lo) copies of a [N, K] weight, pre-scaled by a power of two
     __half *hi = nullptr, *lo = nullptr;
     float inv_scale = 1.f;
@@ -454,16 +468,12 @@ public:
         scan_tc = (D % 64 == 0) && (H % 64 == 0) && (H % scan::UNITS == 0) && (D % scan::PROWS == 0) && (GC + RS * 4 <= num_sms) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
         if (!scan_tc) return;
         const size_t wbytes = std::max<size_t>((size_t)(D / 64) * 16384, (size_t)(H / 64) * 8192);
-        // shared-memory plan (per role): resident weights + activation buffer + (gate: G buffer, c state) + barriers
-        const int KBW = D / 64;
-        scan_kbg = std::max(1, KBW / 4);
-        { int copies = 2 * KBW / scan_kbg; if (KBW % scan_kbg || (copies > scan::GSTAGES && copies % scan::GSTAGES)) scan_kbg = KBW; }
-        const size_t act_gate = std::max<size_t>((size_t)scan::GSTAGES * scan_kbg * 64 * 128, 33280);
-        const size_t act_proj = std::max<size_t>((size_t)2 * (H / 64) * 16 * 128, 33280);
-        const size_t smem_gate = 1024 + (size_t)KBW * 16384 + act_gate + 1024 + (size_t)64 * 256 + (size_t)64 * scan::UNITS * 4 + 256;
-        const size_t smem_proj = 1024 + (size_t)(H / 64) * 8192 + act_proj + 1024 + 256;
+        // shared-memory plan for the largest case (two groups of 32 sessions)
+        const int KBW = D / 64, KBH = H / 64;
+        const size_t smem_gate = 1024 + (size_t)KBW * 16384 + (size_t)scan::GSTAGES * 16384 + 128 * 33 * 4 + 128 + 2 * (size_t)32 * 256 + 2 * (size_t)32 * scan::UNITS * 4 + 512;
+        const size_t smem_proj = 1024 + (size_t)KBH * 8192 + (size_t)KBH * 4096 + 64 * 17 * 4 + 512;
         scan_smem = std::max(smem_gate, smem_proj);
-        if (scan_smem > 227 * 1024 || H / 64 > 256) { scan_tc = false; return; }
+        if (scan_smem > 227 * 1024 || KBH > 256) { scan_tc = false; return; }
         CK(cudaFuncSetAttribute(scan::lstm_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
         for (auto& lw : w.layers) {
             ScanLayer sl;
@@ -489,11 +499,12 @@ public:
             sl.mapWp = make_map_2d(sl.wp, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)RS * 64, (uint64_t)H, 64, 64, true);
             slayers.push_back(sl);
         }
-        CK(cudaMalloc(&sx_h_hi, sizeof(__half) * 64 * (size_t)D)); CK(cudaMalloc(&sx_h_lo, sizeof(__half) * 64 * (size_t)D));
-        CK(cudaMalloc(&sx_m_hi, sizeof(__half) * 64 * (size_t)H)); CK(cudaMalloc(&sx_m_lo, sizeof(__half) * 64 * (size_t)H));
-        CK(cudaMemset(sx_m_hi, 0, sizeof(__half) * 64 * (size_t)H)); CK(cudaMemset(sx_m_lo, 0, sizeof(__half) * 64 * (size_t)H));
-        CK(cudaMalloc(&scan_counters, 2 * sizeof(unsigned)));
-        owned.push_back(sx_h_hi); owned.push_back(sx_h_lo); owned.push_back(sx_m_hi); owned.push_back(sx_m_lo); owned.push_back(scan_counters);
+        // per group: h exchange [2][32][D], m exchange [2][32][H]
+        CK(cudaMalloc(&sx_h_hi, sizeof(__half) * 2 * 2 * 32 * (size_t)D)); sx_h_lo = nullptr;
+        CK(cudaMalloc(&sx_m_hi, sizeof(__half) * 2 * 2 * 32 * (size_t)H)); sx_m_lo = nullptr;
+        CK(cudaMemset(sx_m_hi, 0, sizeof(__half) * 2 * 2 * 32 * (size_t)H));
+        CK(cudaMalloc(&scan_counters, 4 * sizeof(unsigned)));
+        owned.push_back(sx_h_hi); owned.push_back(sx_m_hi); owned.push_back(scan_counters);
     }
 
     void dump_trace(int grid, int T, int GC) {
@@ -519,33 +530,40 @@ public:
         fprintf(stderr, "\n  gate release spread [%.0f, %.0f]  proj release spread [%.0f, %.0f]\n", mn, mx, mn2, mx2);
     }
 
-    // one layer, steps [t0, t0+tc) of this pass: the recurrent scan on tensor cores, 64 sessions at a time
+    // one layer, steps [t0, t0+tc) of this pass: the recurrent scan on tensor cores, 64 sessions (two interleaved groups of 32) per launch
     void scan_layer_tc(int l, const float* G, float* Hout, float* hw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int D = d.D, H = d.H;
         ScanLayer& sl = slayers[(size_t)l];
         for (int g0 = 0; g0 < B; g0 += 64) {
-            const int Bg = std::min(64, B - g0), Bp = (Bg + 15) & ~15;
+            const int Bc = std::min(64, B - g0);
             scan::ScanArgs a{};
-            a.T = tc; a.t0 = t0; a.B = Bg; a.Bp = Bp; a.Bs = B; a.g0 = g0; a.D = D; a.H = H;
-            a.GC = H / scan::UNITS; a.RS = D / scan::PROWS; a.BSP = Bp / 16; a.Np = 16;
-            a.KBG = scan_kbg;
+            a.T = tc; a.t0 = t0; a.NG = Bc > 16 ? 2 : 1;
+            a.Bg[0] = a.NG == 2 ? (Bc + 1) / 2 : Bc; a.Bg[1] = Bc - a.Bg[0];
+            a.goff[0] = 0; a.goff[1] = a.Bg[0];
+            a.Bp = (a.Bg[0] + 15) & ~15;
+            a.Bs = B; a.g0 = g0; a.D = D; a.H = H;
+            a.GC = H / scan::UNITS; a.RS = D / scan::PROWS; a.BSP = a.Bp / 16;
+            const int KBW = D / 64, KBH = H / 64;
+            a.KBG = 1; for (int kk = 1; kk <= KBW; kk++) if (KBW % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
+            a.PC = KBH % 4 == 0 ? 4 : (KBH % 2 == 0 ? 2 : 1);
             a.inv_scale_hh = sl.inv_hh; a.inv_scale_hr = sl.inv_hr;
             a.nsteps = d_nsteps + g0; a.c_state = cw + (size_t)g0 * H; a.h_state = hw + (size_t)g0 * D;
-            a.h_hi = sx_h_hi; a.h_lo = sx_h_lo; a.m_hi = sx_m_hi; a.m_lo = sx_m_lo;
+            for (int g = 0; g < scan::MAXG; g++) { a.h_x[g] = sx_h_hi + (size_t)g * 2 * 32 * D; a.m_x[g] = sx_m_hi + (size_t)g * 2 * 32 * H; }
             a.Hout = Hout + (size_t)g0 * D; a.counters = scan_counters;
             static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
-            const unsigned grid_n = (unsigned)(H / scan::UNITS + (D / scan::PROWS) * (Bp / 16));
+            const unsigned grid = (unsigned)(a.GC + a.NG * a.RS * a.BSP);
             const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
-            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)grid_n * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)grid_n * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
-            scan::scan_prepare_kernel<<<32, 256, 0, st>>>(a.h_state, sx_h_hi, sx_h_lo, Bg, Bp, D); launch_check();
-            CK(cudaMemsetAsync(scan_counters, 0, 2 * sizeof(unsigned), st));
-            CUtensorMap mHh = make_map_kblocks(sx_h_hi, (uint64_t)Bp, (uint64_t)D, (uint32_t)Bp, (uint32_t)scan_kbg);
-            CUtensorMap mHl = make_map_kblocks(sx_h_lo, (uint64_t)Bp, (uint64_t)D, (uint32_t)Bp, (uint32_t)scan_kbg);
-            CUtensorMap mMh = make_map_kblocks(sx_m_hi, (uint64_t)Bp, (uint64_t)H, 16, (uint32_t)(H / 64));
-            CUtensorMap mMl = make_map_kblocks(sx_m_lo, (uint64_t)Bp, (uint64_t)H, 16, (uint32_t)(H / 64));
-            CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, 16, (uint32_t)Bp, false);
-            void* args[] = { &sl.mapWg, &sl.mapWp, &mHh, &mHl, &mMh, &mMl, &mG, &a };
-            const unsigned grid = (unsigned)(a.GC + a.RS * a.BSP);
+            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)grid * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)grid * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
+            for (int g = 0; g < a.NG; g++) { scan::scan_prepare_kernel<<<32, 256, 0, st>>>(a.h_state + (size_t)a.goff[g] * D, a.h_x[g], a.Bg[g], a.Bp, D); launch_check(); }
+            CK(cudaMemsetAsync(sx_m_hi, 0, sizeof(__half) * 2 * 2 * 32 * (size_t)H, st));
+            CK(cudaMemsetAsync(scan_counters, 0, 4 * sizeof(unsigned), st));
+            CUtensorMap mHx[2], mMx[2];
+            for (int g = 0; g < 2; g++) {
+                mHx[g] = make_map_kblocks_hl(a.h_x[g], (uint64_t)a.Bp, (uint64_t)D, (uint32_t)a.Bp, (uint32_t)a.KBG);
+                mMx[g] = make_map_kblocks_hl(a.m_x[g], (uint64_t)a.Bp, (uint64_t)H, 16, (uint32_t)(KBH / a.PC));
+            }
+            CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, 16, (uint32_t)a.Bp, false);
+            void* args[] = { &sl.mapWg, &sl.mapWp, &mHx[0], &mHx[1], &mMx[0], &mMx[1], &mG, &a };
             CK(cudaLaunchCooperativeKernel((const void*)scan::lstm_scan_tc_kernel, dim3(grid), dim3(scan::THREADS), args, scan_smem, st));
             launch_check();
             if (do_trace) dump_trace((int)grid, tc, a.GC);
