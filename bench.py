@@ -175,14 +175,14 @@ def main():
     torch.cuda.set_device(local)
     os.environ["APRIL_B200_DEVICE"] = str(local)
     import april_asr_b200 as A
-    from april_asr_b200 import _ffi
+    from april_asr_b200 import _ffi, dist_util
     from gen_pcm import gen_stream
 
     path = ensure_model(rank, dist)
     lib = A.Lib()
     m = A.Model(path, lib)
     S, n = a.sessions, int(16000 * a.seconds)
-    pcms = [gen_stream(rank * S + i, n) for i in range(S)]
+    pcms = [gen_stream(i, n) for i in dist_util.shard_stream_ids(rank, world, S)]
     handler = ctypes.cast(lib.c.aab_counting_handler, A.HANDLER)
     counters = (ctypes.c_uint64 * 4)()
 
@@ -230,12 +230,7 @@ def main():
     lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
     lib.c.aab_set_timing(m.handle, 0)
 
-    wall_s, compute_s = sum(walls), st.compute_ms / 1e3
-    if dist is not None:
-        t = torch.tensor([wall_s, compute_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall_s, compute_s = float(t[0]), float(t[1])
-    frames_step = S * FRAMES_PER_STREAM(n) * world
+    (wall_s, compute_s), (frames_step,) = dist_util.combine(dist, "cuda", [sum(walls), st.compute_ms / 1e3], [S * FRAMES_PER_STREAM(n)])
     frames_total = frames_step * a.steps
 
     if rank == 0:
@@ -259,9 +254,12 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "time-batched projection GEMMs (W_ih, FF1, FF2, conv-out, enc_proj)",
                          "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": (gemm_tflops / peak_tf) if gemm_tflops else None,
-                         "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
+                         "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                         "traffic": 838.8e6, "traffic_note": "dram bytes read+written by one W_ih launch (M=49664,N=4096,K=512), ncu --set full, profiles/r01_ncu_raw_gemm.csv; algorithmic bytes of that launch: 923e6",
+                         "precision": "fp16x3 split (3 tensor-core MMAs per algorithmic product; tokens identical to the fp32 reference); algorithmic FLOPs counted once",
                          "gemm_ms_per_step": st.gemm_ms / a.steps, "lstm_scan_ms_per_step": st.lstm_scan_ms / a.steps,
                          "whole_pass_tflops": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12,
+                         "lstm_scan": {"bound": "latency", "us_per_layer_step": 1e3 * st.lstm_scan_ms / max(1.0, (st.encoder_steps / S) * 12), "algorithmic_tflops": (st.encoder_steps * 2.0 * 31_457_280) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e12},
                          "whole_pass_frac": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12 / peak_tf},
             "results": {"partial_callbacks": int(counters[0]), "final_callbacks": int(counters[1]), "silence_callbacks": int(counters[2]), "final_tokens": int(counters[3]),
                         "encoder_steps_per_pass": steps_per_pass, "joiner_passes_per_pass": st.joiner_passes / a.steps},
