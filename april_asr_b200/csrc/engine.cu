@@ -12,6 +12,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_scan.cuh"
+#include "kernels_scan2.cuh"
 
 namespace april {
 
@@ -91,6 +92,19 @@ static CUtensorMap make_map_kblocks_hl(const void* ptr, uint64_t rows, uint64_t 
     CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (4-D) failed: %d\n", (int)r); abort(); }
+    return m;
+}
+
+// 5-D view of the scan2 exchange buffer Mx[t][hl][session][H]: {64-wide k-block element, session, hi|lo, k-block, time}
+static CUtensorMap make_map_mx(const void* ptr, uint64_t Bs, uint64_t H, uint64_t Trows, uint32_t box_sessions, uint32_t box_kb) {
+    CUtensorMap m;
+    cuuint64_t dims[5] = { 64, Bs, 2, H / 64, Trows };
+    cuuint64_t strides[4] = { H * sizeof(__half), Bs * H * sizeof(__half), 64 * sizeof(__half), 2 * Bs * H * sizeof(__half) };
+    cuuint32_t box[5] = { 64, box_sessions, 2, box_kb, 1 };
+    cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (5-D) failed: %d\n", (int)r); abort(); }
     return m;
 }
 
@@ -178,6 +192,13 @@ public:
     struct ScanLayer { __half *wg = nullptr, *wp = nullptr; float inv_hh = 1.f, inv_hr = 1.f; CUtensorMap mapWg, mapWp; };
     std::vector<ScanLayer> slayers;
     bool scan_tc = false;
+    // single-exchange scan (kernels_scan2.cuh): W_eff = W_hh W_hr slices + W_hr for the layer-output GEMM; recurrent state is m
+    struct Scan2Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; };
+    std::vector<Scan2Layer> s2layers;
+    bool scan2 = false;
+    size_t scan2_smem = 0;
+    float* m_store = nullptr;       // [slot][L][H]
+    DevBuf b_mx, b_mall_h, b_mall_l, b_mw;
     __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
     unsigned* scan_counters = nullptr;
     size_t scan_smem = 0;
@@ -258,6 +279,7 @@ public:
             }
             set_gemm_attrs();
             init_scan(w);
+            init_scan2(w);
         }
 
         // vocabulary flags (april_session.c:338-351)
@@ -367,7 +389,7 @@ public:
         cudaSetDevice(dev);
         if (st) cudaStreamSynchronize(st);
         for (void* p : owned) cudaFree(p);
-        cudaFree(dout_blank); cudaFree(dtab); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
+        cudaFree(dout_blank); cudaFree(dtab); cudaFree(m_store); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -384,6 +406,7 @@ public:
     void grow_slots(int new_cap) {
         size_t o = (size_t)slot_cap, n = (size_t)new_cap;
         regrow(h_store, o * d.L * d.D, n * d.L * d.D);
+        regrow(m_store, o * d.L * d.H, n * d.L * d.H);
         regrow(c_store, o * d.L * d.H, n * d.L * d.H);
         regrow(dout_store, o * d.J, n * d.J);
         regrow(carry_store, o * CARRY_CAP * d.MEL, n * CARRY_CAP * d.MEL);
@@ -401,6 +424,7 @@ public:
         // zero h/c (calloc'ed tensors, ort_util.h:48-50), context = blanks + decoder output (april_session.c:432-438)
         CK(cudaMemsetAsync(h_store + (size_t)s * d.L * d.D, 0, sizeof(float) * (size_t)d.L * d.D, st));
         CK(cudaMemsetAsync(c_store + (size_t)s * d.L * d.H, 0, sizeof(float) * (size_t)d.L * d.H, st));
+        CK(cudaMemsetAsync(m_store + (size_t)s * d.L * d.H, 0, sizeof(float) * (size_t)d.L * d.H, st));
         k::GreedyState g{};
         g.ctx0 = g.ctx1 = prm.blank_id;
         CK(cudaMemcpyAsync(gstate + s, &g, sizeof g, cudaMemcpyHostToDevice, st));
@@ -530,6 +554,74 @@ public:
         fprintf(stderr, "\n  gate release spread [%.0f, %.0f]  proj release spread [%.0f, %.0f]\n", mn, mx, mn2, mx2);
     }
 
+    void init_scan2(const ModelWeights& w) {
+        const int D = d.D, H = d.H;
+        const char* sel = getenv("APRIL_B200_SCAN");
+        scan2 = (H % 64 == 0) && (H % scan2::UNITS == 0) && (H / scan2::UNITS <= num_sms) && (D % 8 == 0) && !(sel && !strcmp(sel, "v1")) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
+        if (!scan2) return;
+        const int KBH = H / 64, GC = H / scan2::UNITS;
+        scan2_smem = 1024 + (size_t)KBH * 8192 + std::max<size_t>((size_t)scan2::RSTAGES * 32768, 64 * 65 * 4) + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + 512;
+        if (scan2_smem > 227 * 1024) { scan2 = false; return; }
+        CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan2_smem));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
+        float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+        CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
+        std::vector<float> weff((size_t)4 * H * H);
+        for (auto& lw : w.layers) {
+            Scan2Layer sl;
+            CK(cudaMemcpy(dA, lw.w_hh.data(), sizeof(float) * (size_t)4 * H * D, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dB, lw.w_hr.data(), sizeof(float) * (size_t)D * H, cudaMemcpyHostToDevice));
+            scan2::weff_kernel<<<dim3((unsigned)((H + 15) / 16), (unsigned)((4 * H + 15) / 16)), 256, 0, st>>>(dA, dB, dC, 4 * H, H, D);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(weff.data(), dC, sizeof(float) * weff.size(), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const float sc = pow2_scale(weff, sl.inv);
+            std::vector<__half> wg((size_t)GC * 64 * H);
+            for (int c = 0; c < GC; c++)
+                for (int g4 = 0; g4 < 4; g4++)
+                    for (int u = 0; u < scan2::UNITS; u++) {
+                        const float* src = weff.data() + ((size_t)g4 * H + (size_t)c * scan2::UNITS + u) * H;
+                        __half* hi = wg.data() + ((size_t)c * 64 + g4 * 8 + u) * H;
+                        __half* lo = wg.data() + ((size_t)c * 64 + 32 + g4 * 8 + u) * H;
+                        for (int k = 0; k < H; k++) { float x = src[k] * sc; __half hh = __float2half_rn(x); hi[k] = hh; lo[k] = __float2half_rn(x - __half2float(hh)); }
+                    }
+            sl.w = upload(wg);
+            sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 64, (uint64_t)H, 64, 64, true);
+            sl.w_hr = make_tc_weight(lw.w_hr, D, H);
+            s2layers.push_back(sl);
+        }
+        CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
+        if (!scan_counters) { CK(cudaMalloc(&scan_counters, 4 * sizeof(unsigned))); owned.push_back(scan_counters); }
+    }
+
+    // one layer, steps [t0, t0+tc): single-exchange scan; writes m rows (Mall) for the layer-output GEMM
+    void scan2_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
+        const int H = d.H;
+        Scan2Layer& sl = s2layers[(size_t)l];
+        __half* Mx = b_mx.as<__half>();
+        scan2::scan2_prepare_kernel<<<64, 256, 0, st>>>(mw, Mx, B, H); launch_check();
+        for (int g0 = 0; g0 < B; g0 += 64) {
+            const int Bc = std::min(64, B - g0);
+            scan2::Scan2Args a{};
+            a.T = tc; a.t0 = t0; a.B = Bc; a.Bp = (Bc + 15) & ~15; a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan2::UNITS;
+            const int KBH = H / 64;
+            a.KBG = 1; for (int kk = 1; kk <= KBH; kk++) if (KBH % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 32768) a.KBG = kk;
+            a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.c_state = cw; a.m_state = mw;
+            a.Mx = Mx; a.Mall_hi = b_mall_h.as<__half>(); a.Mall_lo = b_mall_l.as<__half>(); a.counter = scan_counters;
+            static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
+            const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
+            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
+            CK(cudaMemsetAsync(scan_counters, 0, 4 * sizeof(unsigned), st));
+            CUtensorMap mMx = make_map_mx(Mx, (uint64_t)B, (uint64_t)H, (uint64_t)tc + 1, (uint32_t)a.Bp, (uint32_t)a.KBG);
+            CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, scan2::UNITS, (uint32_t)a.Bp, false);
+            void* args[] = { &sl.mapW, &mMx, &mG, &a };
+            CK(cudaLaunchCooperativeKernel((const void*)scan2::lstm_scan2_kernel, dim3((unsigned)a.GC), dim3(scan2::THREADS), args, scan2_smem, st));
+            launch_check();
+            if (do_trace) dump_trace(a.GC, tc, a.GC / 2);
+        }
+    }
+
     // one layer, steps [t0, t0+tc) of this pass: the recurrent scan on tensor cores, 64 sessions (two interleaved groups of 32) per launch
     void scan_layer_tc(int l, const float* G, float* Hout, float* hw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int D = d.D, H = d.H;
@@ -593,11 +685,13 @@ public:
             const size_t sm = tc::GemmCfg<3>::SMEM_BYTES;
             if (epi == tc::GE_F32) tc::gemm_tc_kernel<3, tc::GE_F32><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
             else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            else if (epi == tc::GE_F32_RESIDUAL_SPLIT) tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
             else tc::gemm_tc_kernel<3, tc::GE_DSWISH_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
         } else {
             const size_t sm = tc::GemmCfg<1>::SMEM_BYTES;
             if (epi == tc::GE_F32) tc::gemm_tc_kernel<1, tc::GE_F32><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
             else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            else if (epi == tc::GE_F32_RESIDUAL_SPLIT) tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
             else tc::gemm_tc_kernel<1, tc::GE_DSWISH_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
         }
         launch_check();
@@ -792,6 +886,11 @@ public:
             b_g.ensure(sizeof(float) * Mc * 4 * H); b_hout.ensure(sizeof(float) * Mc * D); b_f1.ensure(sizeof(float) * Mc * F);
             b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
             b_eo.ensure(sizeof(float) * Mc * J);
+            const bool use_s2 = npass && scan2;
+            if (use_s2) {
+                b_mx.ensure(sizeof(__half) * ((size_t)Tc + 1) * 2 * B * H); b_mall_h.ensure(sizeof(__half) * Mc * H); b_mall_l.ensure(sizeof(__half) * Mc * H);
+            }
+            b_mw.ensure(sizeof(float) * (size_t)L * B * H);
             if (npass) {
                 b_xe_h.ensure(sizeof(__half) * Mc * KE); b_xe_l.ensure(sizeof(__half) * Mc * KE);
                 b_x_h.ensure(sizeof(__half) * Mc * D); b_x_l.ensure(sizeof(__half) * Mc * D);
@@ -807,6 +906,8 @@ public:
                   *F1 = b_f1.as<float>(), *Ms = b_m.as<float>(), *Hw = b_hw.as<float>(), *Cw = b_cw.as<float>(), *EO = b_eo.as<float>();
             k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
             k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
+            float* Mw = b_mw.as<float>();
+            if (use_s2) { k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
             const size_t greedy_smem = sizeof(float) * (size_t)(3 * J + d.E);
             for (int t0 = 0; t0 < Tmax; t0 += Tc) {
                 const int tc = std::min(Tc, Tmax - t0);
@@ -828,7 +929,8 @@ public:
                     float* hw = Hw + (size_t)l * B * D;
                     float* cw = Cw + (size_t)l * B * H;
                     span_begin(1);
-                    if (npass && scan_tc) scan_layer_tc(l, G, Hout, hw, cw, d_nsteps, t0, tc, B);
+                    if (use_s2) scan2_layer(l, G, Mw + (size_t)l * B * H, cw, d_nsteps, t0, tc, B);
+                    else if (npass && scan_tc) scan_layer_tc(l, G, Hout, hw, cw, d_nsteps, t0, tc, B);
                     else for (int t = 0; t < tc; t++) {
                         k::lstm_gates_kernel<<<dim3((unsigned)(H / 16), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
                             G + (size_t)t * B * 4 * H, hw, w.w_hh, cw, Ms, d_nsteps, t0 + t, B, D, H);
@@ -846,7 +948,8 @@ public:
                         k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
                     } else {
                         const TcLayer& tl = tlayers[(size_t)l];
-                        tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check();
+                        if (use_s2) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>(), b_mall_l.as<__half>(), s2layers[(size_t)l].w_hr, nullptr, X, X1, X1_h, X1_l, M);   // x + W_hr m
+                        else { tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check(); }
                         gemm_tc(tc::GE_DSWISH_SPLIT, X1_h, X1_l, tl.ff1, w.ff1_b, nullptr, nullptr, F1_h, F1_l, M);
                         gemm_tc(tc::GE_F32_RESIDUAL, F1_h, F1_l, tl.ff2, w.ff2_b, X1, X2, nullptr, nullptr, M);
                         tc::basic_norm_split_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, X_h, X_l, M, D, w.norm_eps); launch_check();
@@ -870,6 +973,7 @@ public:
             }
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
+            if (use_s2) { k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
             p_rec.ensure(rec_bytes); p_np.ensure(np_bytes);
             CK(cudaMemcpyAsync(p_rec.p, b_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(p_np.p, b_np.p, np_bytes, cudaMemcpyDeviceToHost, st));

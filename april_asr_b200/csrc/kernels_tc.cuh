@@ -122,7 +122,8 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 // ------------------------------------------------------------------------------------------------
 enum GemmEpi { GE_F32 = 0,            // out_f32 = v
                GE_F32_RESIDUAL = 1,   // out_f32 = v + R
-               GE_DSWISH_SPLIT = 2 }; // (out_hi, out_lo) = split(double_swish(v))
+               GE_DSWISH_SPLIT = 2,   // (out_hi, out_lo) = split(double_swish(v))
+               GE_F32_RESIDUAL_SPLIT = 3 }; // out_f32 = v + R, and (out_hi, out_lo) = split(out_f32)
 
 struct GemmArgs {
     int M, N, K;
@@ -256,13 +257,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                         for (int e = 0; e < 8; e++) x[e] = v[j + e] * g.inv_scale + (g.bias ? __ldg(g.bias + nb + j + e) : 0.f);
                         const size_t off = (size_t)m * g.N + nb + j;
-                        if (EPI == GE_F32 || EPI == GE_F32_RESIDUAL) {
-                            if (EPI == GE_F32_RESIDUAL) {
+                        if (EPI == GE_F32 || EPI == GE_F32_RESIDUAL || EPI == GE_F32_RESIDUAL_SPLIT) {
+                            if (EPI == GE_F32_RESIDUAL || EPI == GE_F32_RESIDUAL_SPLIT) {
                                 const float4 r0 = *reinterpret_cast<const float4*>(g.residual + off), r1 = *reinterpret_cast<const float4*>(g.residual + off + 4);
                                 x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w; x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
                             }
                             *reinterpret_cast<float4*>(g.out_f32 + off) = make_float4(x[0], x[1], x[2], x[3]);
                             *reinterpret_cast<float4*>(g.out_f32 + off + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                            if (EPI == GE_F32_RESIDUAL_SPLIT) {
+                                __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                                for (int e = 0; e < 8; e++) split_f16(x[e], hi[e], lo[e]);
+                                *reinterpret_cast<uint4*>(g.out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+                                *reinterpret_cast<uint4*>(g.out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+                            }
                         } else {
                             __align__(16) __half hi[8], lo[8];
 #pragma unroll
