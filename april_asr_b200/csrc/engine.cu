@@ -197,6 +197,7 @@ public:
     std::vector<Scan2Layer> s2layers;
     bool scan2 = false;
     size_t scan2_smem = 0;
+    int scan2_cs = 1;               // thread-block cluster size of the scan (TMA multicast factor)
     float* m_store = nullptr;       // [slot][L][H]
     DevBuf b_mx, b_mall_h, b_mall_l, b_mw;
     __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
@@ -560,7 +561,7 @@ public:
         scan2 = (H % 64 == 0) && (H % scan2::UNITS == 0) && (H / scan2::UNITS <= num_sms) && (D % 8 == 0) && !(sel && !strcmp(sel, "v1")) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
         if (!scan2) return;
         const int KBH = H / 64, GC = H / scan2::UNITS;
-        scan2_smem = 1024 + (size_t)KBH * 8192 + std::max<size_t>((size_t)scan2::RSTAGES * 32768, 64 * 65 * 4) + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + 512;
+        scan2_smem = 1024 + (size_t)KBH * 8192 + (size_t)scan2::RSTAGES * 16384 + 64 * 65 * 4 + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + 512;
         if (scan2_smem > 227 * 1024) { scan2 = false; return; }
         CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan2_smem));
         CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
@@ -592,6 +593,23 @@ public:
             s2layers.push_back(sl);
         }
         CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
+        // largest cluster size whose clusters can all be co-resident (the kernel spin-waits across the grid)
+        scan2_cs = 1;
+        const char* cs_env = getenv("APRIL_B200_SCAN_CLUSTER");        // multicast is opt-in: it measured slower than plain loads
+        for (int cs : { 8, 4, 2 }) {
+            if (!cs_env || atoi(cs_env) != cs) continue;
+            if (GC % cs) continue;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan2::THREADS); cfg.dynamicSmemBytes = scan2_smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cs > 8) CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            if (cudaOccupancyMaxActiveClusters(&ncl, scan2::lstm_scan2_kernel, &cfg) == cudaSuccess && ncl * cs >= GC) { scan2_cs = cs; break; }
+            cudaGetLastError();
+        }
+        if (cs_env && atoi(cs_env) == 1) scan2_cs = 1;
         if (!scan_counters) { CK(cudaMalloc(&scan_counters, 4 * sizeof(unsigned))); owned.push_back(scan_counters); }
     }
 
@@ -604,9 +622,14 @@ public:
         for (int g0 = 0; g0 < B; g0 += 64) {
             const int Bc = std::min(64, B - g0);
             scan2::Scan2Args a{};
-            a.T = tc; a.t0 = t0; a.B = Bc; a.Bp = (Bc + 15) & ~15; a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan2::UNITS;
+            static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 1;
+            a.T = tc; a.t0 = t0; a.NG = (groups_env == 2 && Bc > 16) ? 2 : 1;
+            a.Bg[0] = a.NG == 2 ? (Bc + 1) / 2 : Bc; a.Bg[1] = Bc - a.Bg[0];
+            a.goff[0] = 0; a.goff[1] = a.Bg[0];
+            a.Bp = (a.Bg[0] + 15) & ~15;
+            a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan2::UNITS;
             const int KBH = H / 64;
-            a.KBG = 1; for (int kk = 1; kk <= KBH; kk++) if (KBH % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 32768) a.KBG = kk;
+            a.KBG = 1; for (int kk = 1; kk <= KBH; kk++) if (KBH % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
             a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.c_state = cw; a.m_state = mw;
             a.Mx = Mx; a.Mall_hi = b_mall_h.as<__half>(); a.Mall_lo = b_mall_l.as<__half>(); a.counter = scan_counters;
             static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
@@ -615,8 +638,15 @@ public:
             CK(cudaMemsetAsync(scan_counters, 0, 4 * sizeof(unsigned), st));
             CUtensorMap mMx = make_map_mx(Mx, (uint64_t)B, (uint64_t)H, (uint64_t)tc + 1, (uint32_t)a.Bp, (uint32_t)a.KBG);
             CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, scan2::UNITS, (uint32_t)a.Bp, false);
-            void* args[] = { &sl.mapW, &mMx, &mG, &a };
-            CK(cudaLaunchCooperativeKernel((const void*)scan2::lstm_scan2_kernel, dim3((unsigned)a.GC), dim3(scan2::THREADS), args, scan2_smem, st));
+            {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan2::THREADS); cfg.dynamicSmemBytes = scan2_smem; cfg.stream = st;
+                cudaLaunchAttribute at[2];
+                at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+                at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = (unsigned)scan2_cs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 2;
+                CK(cudaLaunchKernelEx(&cfg, scan2::lstm_scan2_kernel, sl.mapW, mMx, mG, a));
+            }
             launch_check();
             if (do_trace) dump_trace(a.GC, tc, a.GC / 2);
         }
