@@ -185,7 +185,10 @@ public:
     float out_norm_eps = 0.f;
     std::vector<DeviceLayer> layers;
     int npass = 3;                  // 0: exact fp32 SIMT tier; 1: fp16 tensor cores; 3: fp16x3 split (default)
-    TcWeight tw_out, tw_proj;
+    TcWeight tw_out, tw_proj, tw_conv3, tw_out_perm;
+    tc::Conv12Params c12{};
+    bool conv_tc = false;
+    DevBuf b_a3_h, b_a3_l;
     struct TcLayer { TcWeight w_ih, ff1, ff2; };
     std::vector<TcLayer> tlayers;
     // persistent tensor-core scan: stacked (hi;lo) recurrent weights per layer + exchange buffers
@@ -271,6 +274,19 @@ public:
             if (d.D % 8 || d.H % 8 || d.F % 8 || d.J % 8) { err = "tensor-core tier needs dims that are multiples of 8"; return false; }
             tw_out = make_tc_weight(w.out_w, d.D, d.C3 * d.F3);
             tw_proj = make_tc_weight(w.enc_proj_w, d.J, d.D);
+            // conv3 and the subsampler's linear as GEMMs (kernels_tc.cuh: conv12_im2col_kernel)
+            conv_tc = (d.C2 % 8 == 0) && ((d.C2 * 9) % 8 == 0) && (d.C3 % 8 == 0) && ((d.SEG - 2 - 3) / 2 + 1 == 3) && getenv("APRIL_B200_SIMT_CONV") == nullptr;
+            if (conv_tc) {
+                tw_conv3 = make_tc_weight(w.conv3_w, d.C3, d.C2 * 9);                    // [oc][ic*9 + ky*3 + kx]
+                std::vector<float> perm((size_t)d.D * d.C3 * d.F3);
+                for (int n = 0; n < d.D; n++) for (int c = 0; c < d.C3; c++) for (int f = 0; f < d.F3; f++)
+                    perm[(size_t)n * d.C3 * d.F3 + (size_t)f * d.C3 + c] = w.out_w[(size_t)n * d.C3 * d.F3 + (size_t)c * d.F3 + f];
+                tw_out_perm = make_tc_weight(perm, d.D, d.C3 * d.F3);
+                std::vector<float> w2t((size_t)d.C1 * 9 * d.C2);
+                for (int oc = 0; oc < d.C2; oc++) for (int ic = 0; ic < d.C1; ic++) for (int k9 = 0; k9 < 9; k9++)
+                    w2t[((size_t)ic * 9 + k9) * d.C2 + oc] = w.conv2_w[((size_t)oc * d.C1 + ic) * 9 + k9];
+                c12.w2t = upload(w2t);
+            }
             for (auto& lw : w.layers) {
                 TcLayer tl;
                 tl.w_ih = make_tc_weight(lw.w_ih, 4 * d.H, d.D);
@@ -352,6 +368,9 @@ public:
         cp.T1 = d.SEG - 2; cp.F1 = d.MEL - 2; cp.T2 = (cp.T1 - 3) / 2 + 1; cp.F2 = (cp.F1 - 3) / 2 + 1; cp.F3 = d.F3;
         cp.w1 = conv1_w; cp.b1 = conv1_b; cp.w2 = conv2_w; cp.b2 = conv2_b; cp.w3 = conv3_w; cp.b3 = conv3_b;
         CK(cudaFuncSetAttribute(k::conv_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem()));
+        c12.SEG = cp.SEG; c12.MEL = cp.MEL; c12.STEP = cp.STEP; c12.C1 = cp.C1; c12.C2 = cp.C2; c12.T1 = cp.T1; c12.F1 = cp.F1; c12.T2 = cp.T2; c12.F2 = cp.F2; c12.F3 = cp.F3;
+        c12.w1 = conv1_w; c12.b1 = conv1_b; c12.b2 = conv2_b;
+        CK(cudaFuncSetAttribute(tc::conv12_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem()));
 
         CK(cudaMalloc(&dout_blank, sizeof(float) * (size_t)d.J));
         k::decoder_kernel<<<1, 256, (size_t)(d.E + d.J) * sizeof(float), st>>>(jp, prm.blank_id, prm.blank_id, dout_blank);
@@ -622,7 +641,7 @@ public:
         for (int g0 = 0; g0 < B; g0 += 64) {
             const int Bc = std::min(64, B - g0);
             scan2::Scan2Args a{};
-            static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 1;
+            static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 2;
             a.T = tc; a.t0 = t0; a.NG = (groups_env == 2 && Bc > 16) ? 2 : 1;
             a.Bg[0] = a.NG == 2 ? (Bc + 1) / 2 : Bc; a.Bg[1] = Bc - a.Bg[0];
             a.goff[0] = 0; a.goff[1] = a.Bg[0];
@@ -923,6 +942,7 @@ public:
             b_mw.ensure(sizeof(float) * (size_t)L * B * H);
             if (npass) {
                 b_xe_h.ensure(sizeof(__half) * Mc * KE); b_xe_l.ensure(sizeof(__half) * Mc * KE);
+                if (conv_tc) { b_a3_h.ensure(sizeof(__half) * Mc * d.F3 * d.C2 * 9); b_a3_l.ensure(sizeof(__half) * Mc * d.F3 * d.C2 * 9); }
                 b_x_h.ensure(sizeof(__half) * Mc * D); b_x_l.ensure(sizeof(__half) * Mc * D);
                 b_x1_h.ensure(sizeof(__half) * Mc * D); b_x1_l.ensure(sizeof(__half) * Mc * D);
                 b_f1_h.ensure(sizeof(__half) * Mc * F); b_f1_l.ensure(sizeof(__half) * Mc * F);
@@ -942,12 +962,19 @@ public:
             for (int t0 = 0; t0 < Tmax; t0 += Tc) {
                 const int tc = std::min(Tc, Tmax - t0);
                 const int M = tc * B;
-                k::conv_embed_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(cp, FB, row_pitch, d_nsteps, t0, B, Xe); launch_check();
                 const unsigned ew_grid = (unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, (size_t)num_sms * 8);
                 if (npass == 0) {
+                    k::conv_embed_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(cp, FB, row_pitch, d_nsteps, t0, B, Xe); launch_check();
                     gemm(k::EPI_BIAS, Xe, out_w, out_b, nullptr, X1, M, D, KE);
                     k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, M, D, out_norm_eps); launch_check();
+                } else if (conv_tc) {
+                    // conv1/conv2 + im2col (SIMT), conv3 as a GEMM with fused DoubleSwish + split, then the linear on permuted weights
+                    tc::conv12_im2col_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(c12, FB, row_pitch, d_nsteps, t0, B, b_a3_h.as<__half>(), b_a3_l.as<__half>()); launch_check();
+                    gemm_tc(tc::GE_DSWISH_SPLIT, b_a3_h.as<__half>(), b_a3_l.as<__half>(), tw_conv3, conv3_b, nullptr, nullptr, Xe_h, Xe_l, M * d.F3);
+                    gemm_tc(tc::GE_F32, Xe_h, Xe_l, tw_out_perm, out_b, nullptr, X1, nullptr, nullptr, M);
+                    tc::basic_norm_split_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, X_h, X_l, M, D, out_norm_eps); launch_check();
                 } else {
+                    k::conv_embed_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(cp, FB, row_pitch, d_nsteps, t0, B, Xe); launch_check();
                     tc::split_rows_kernel<<<(unsigned)std::min<size_t>(((size_t)M * KE / 4 + 255) / 256, (size_t)num_sms * 8), 256, 0, st>>>(Xe, Xe_h, Xe_l, (size_t)M * KE); launch_check();
                     gemm_tc(tc::GE_F32, Xe_h, Xe_l, tw_out, out_b, nullptr, X1, nullptr, nullptr, M);
                     tc::basic_norm_split_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X1, X, X_h, X_l, M, D, out_norm_eps); launch_check();

@@ -342,5 +342,83 @@ __global__ void basic_norm_split_kernel(const float* __restrict__ X, float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// E1 front half for the tensor-core tier: conv1 + conv2 (fp32 SIMT, 0.3 MMAC per window) and the im2col of
+// conv3's input written as fp16 (hi, lo) rows, so that conv3 (0.66 MMAC per window, 68 % of the subsampler)
+// and the following 2304 -> D linear both run as tcgen05 GEMMs:
+//   A3[(w * F3 + f)][ic * 9 + ky * 3 + kx] = c2[ic][ky][2 f + kx]        (conv3: kernel 3x3, stride 2, T3 == 1)
+// conv3's GEMM output row (w, f) x C3 channels is, read as [w][f * C3 + c], the input of the linear with its
+// weight columns permuted from (c * F3 + f) to (f * C3 + c) at load time (icefall Conv2dSubsampling:
+// x.transpose(1, 2).view(b, t, c * f) [external]).
+// One CTA per (session, step) window; 256 threads.
+// ------------------------------------------------------------------------------------------------
+struct Conv12Params {
+    int SEG, MEL, STEP, C1, C2, T1, F1, T2, F2, F3;
+    const float *w1, *b1, *w2t /*[C1*9][C2] transposed*/, *b2;
+};
+
+__global__ void __launch_bounds__(256)
+conv12_im2col_kernel(Conv12Params P, const float* __restrict__ FB, int row_pitch, const int* __restrict__ nsteps, int t0, int B,
+                     __half* __restrict__ A_hi, __half* __restrict__ A_lo) {
+    extern __shared__ float smem_c[];
+    const int b = blockIdx.x, t = blockIdx.y;
+    const int K3 = P.C2 * 9;
+    const size_t row0 = ((size_t)t * B + b) * P.F3;
+    if (t0 + t >= nsteps[b]) {                                       // ragged tail: defined (zero) rows
+        for (int i = threadIdx.x; i < P.F3 * K3; i += blockDim.x) { A_hi[row0 * K3 + i] = __float2half(0.f); A_lo[row0 * K3 + i] = __float2half(0.f); }
+        return;
+    }
+    float* in = smem_c;                                   // [SEG][MEL]
+    float* c1 = in + P.SEG * P.MEL;                       // [C1][T1][F1]
+    float* c2 = c1 + P.C1 * P.T1 * P.F1;                  // [C2][T2][F2]
+    float* w2s = c2 + P.C2 * P.T2 * P.F2;                 // [C1*9][C2]
+    const float* src = FB + ((size_t)b * row_pitch + (size_t)(t0 + t) * P.STEP) * P.MEL;
+    for (int i = threadIdx.x; i < P.SEG * P.MEL; i += blockDim.x) in[i] = src[i];
+    for (int i = threadIdx.x; i < P.C1 * 9 * P.C2; i += blockDim.x) w2s[i] = P.w2t[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.C1 * P.T1 * P.F1; i += blockDim.x) {
+        const int f = i % P.F1, y = (i / P.F1) % P.T1, c = i / (P.F1 * P.T1);
+        const float* w = P.w1 + c * 9;
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) s = fmaf(in[(y + ky) * P.MEL + f + kx], __ldg(w + ky * 3 + kx), s);
+        c1[i] = dswish_f(s + __ldg(P.b1 + c));
+    }
+    __syncthreads();
+    // conv2: work item = (position p = y * F2 + x, group of 8 output channels): inputs loaded once, weights as float4
+    const int npos = P.T2 * P.F2, ngrp = P.C2 / 8;
+    for (int wi = threadIdx.x; wi < npos * ngrp; wi += blockDim.x) {
+        const int p = wi % npos, cg = wi / npos;
+        const int y = p / P.F2, x = p % P.F2;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[e] = 0.f;
+        for (int ic = 0; ic < P.C1; ic++) {
+            const float* ip = c1 + (ic * P.T1 + 2 * y) * P.F1 + 2 * x;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float v = ip[(k / 3) * P.F1 + (k % 3)];
+                const float4 wa = *reinterpret_cast<const float4*>(w2s + (ic * 9 + k) * P.C2 + cg * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(w2s + (ic * 9 + k) * P.C2 + cg * 8 + 4);
+                acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]); acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
+                acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]); acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) { const int oc = cg * 8 + e; c2[(oc * P.T2 + y) * P.F2 + x] = dswish_f(acc[e] + __ldg(P.b2 + oc)); }
+    }
+    __syncthreads();
+    // im2col rows of conv3 (T3 == 1: ky indexes the 3 rows of c2 directly)
+    for (int i = threadIdx.x; i < P.F3 * K3; i += blockDim.x) {
+        const int f = i / K3, col = i % K3;
+        const int ic = col / 9, ky = (col % 9) / 3, kx = col % 3;
+        const float v = c2[(ic * P.T2 + ky) * P.F2 + 2 * f + kx];
+        __half h, l; split_f16(v, h, l);
+        A_hi[row0 * K3 + i] = h; A_lo[row0 * K3 + i] = l;
+    }
+}
+
 }  // namespace tc
 }  // namespace april
