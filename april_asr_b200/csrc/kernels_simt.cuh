@@ -717,13 +717,18 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
         __syncthreads();
         for (int pass = 0; pass < 3; pass++) {
             // --- A: decoder rows for changed contexts (table lookup = aas_run_decoder), z = tanh(e + d); prefetch next step's e
-            float e_pf[GC_MAX_S][2];
+            float e_pf[GC_MAX_S][2];                                          // registers: fully unrolled, statically indexed
             const bool do_pf = pass == 0 && t + 1 < t_end;
-            for (int s = 0; s < ns; s++) {
-                if (do_pf && t + 1 < s_n[s]) {
+            if (do_pf) {
 #pragma unroll
-                    for (int u = 0; u < 2; u++) { const int j = threadIdx.x + u * 256; e_pf[s][u] = j < J ? enc_out[((size_t)(t + 1 - t_base) * B + s0 + s) * J + j] : 0.f; }
-                }
+                for (int s = 0; s < GC_MAX_S; s++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int j = threadIdx.x + u * 256;
+                        e_pf[s][u] = (s < ns && j < J && t + 1 < s_n[s]) ? enc_out[((size_t)(t + 1 - t_base) * B + s0 + s) * J + j] : 0.f;
+                    }
+            }
+            for (int s = 0; s < ns; s++) {
                 if (s_done[s]) continue;
                 const bool nc = s_newctx[s] != 0;
                 const float* drow = dtab + ((size_t)st[s].ctx0 * V + st[s].ctx1) * J;
@@ -756,11 +761,12 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
                 const int lr = warp * GC_RPW + lane / GC_SG, sq = sg + lane % GC_SG;
                 if (lr < R && sq < ns) logit_s[sq * Rp + lr] = tot + bias_r;
             }
-            if (do_pf && J <= 512)
-                for (int s = 0; s < ns; s++) if (t + 1 < s_n[s]) {
+            if (do_pf) {
 #pragma unroll
-                    for (int u = 0; u < 2; u++) { const int j = threadIdx.x + u * 256; if (j < J) e_nxt[(size_t)s * J + j] = e_pf[s][u]; }
-                }
+                for (int s = 0; s < GC_MAX_S; s++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) { const int j = threadIdx.x + u * 256; if (s < ns && j < J && t + 1 < s_n[s]) e_nxt[(size_t)s * J + j] = e_pf[s][u]; }
+            }
             __syncthreads();
             // --- C: warp s = local arg-max of session s over my rows (ties -> lowest index), published to all 8 CTAs over DSMEM
             if (warp < ns && !s_done[warp]) {
