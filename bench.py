@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--cpu-seconds", type=float, default=2.0, help="audio seconds per session in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="bulk", choices=["bulk", "stream"], help="stream = BASELINE configs[3]: 40 ms chunks through the batched feed, per-chunk latency")
+    ap.add_argument("--ticks", type=int, default=250)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -213,6 +215,33 @@ def main():
             lib.c.aas_free(h)
         return dt
 
+    if a.mode == "stream":
+        # BASELINE configs[3]: S sessions fed 40 ms (640-sample) chunks; latency = time inside one batched feed call
+        # (handlers run before it returns), measured on the host around the C-ABI call.
+        ss = make_sessions()
+        arr = hs_t(*ss)
+        chunk = 640
+        lat = []
+        for k in range(a.ticks + 20):
+            off = (k * chunk) % (n - chunk)
+            p2 = (ctypes.POINTER(ctypes.c_short) * S)(*[ctypes.cast(p.ctypes.data + 2 * off, ctypes.POINTER(ctypes.c_short)) for p in pcms])
+            c2 = (ctypes.c_size_t * S)(*([chunk] * S))
+            t0 = time.perf_counter()
+            rc = lib.c.aab_feed_pcm16_batch(arr, p2, c2, S)
+            dt = time.perf_counter() - t0
+            assert rc == 0
+            if k >= 20:
+                lat.append(dt * 1e3)
+        lat.sort()
+        p50, p99 = lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))]
+        if rank == 0:
+            print(json.dumps({"metric": "chunk_latency_ms", "mode": "stream", "sessions": S, "chunk_ms": 40, "ticks": a.ticks, "p50_ms": p50, "p99_ms": p99,
+                              "mean_ms": sum(lat) / len(lat), "frames_per_sec": S * 4 / (sum(lat) / len(lat) / 1e3), "x_realtime_per_stream": 40.0 / (sum(lat) / len(lat)),
+                              "config": {"workload": "%d sessions streaming 40 ms chunks through aab_feed_pcm16_batch (BASELINE configs[3]), 1 GPU" % S}}))
+        for h in ss:
+            lib.c.aas_free(h)
+        m.close()
+        return
     for _ in range(a.warmup):
         one_step()
     st = _ffi.AprilB200Stats()

@@ -149,3 +149,21 @@ def test_async_session_batcher():
     for s in ss:
         s.close()
     m.close()
+
+
+def test_reference_example_cpp_unmodified_against_this_library(tmp_path):
+    """/root/reference/example.cpp compiled UNMODIFIED twice (oracle/Makefile): against the oracle library and against
+    libaprilasr.so. Same PCM, same model -> byte-identical stdout (partials, finals, silences as the CLI prints them)."""
+    import subprocess
+    ref = os.path.join(C.ROOT, "oracle", "_ref", "example_ref")
+    mine = os.path.join(C.ROOT, "oracle", "_ref", "example_b200")
+    if not (os.path.exists(ref) and os.path.exists(mine)):
+        pytest.skip("example binaries not built (need /root/reference at build time)")
+    pcm = C.gen_stream(0, 96000)
+    raw = tmp_path / "a.raw"
+    raw.write_bytes(pcm.tobytes())
+    a = subprocess.run([ref, str(raw), C.TINY_MODEL], capture_output=True, timeout=300)
+    b = subprocess.run([mine, str(raw), C.TINY_MODEL], capture_output=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr[-300:], b.stderr[-300:])
+    assert a.stdout == b.stdout
+    assert b"Model name: synthetic-tiny" in b.stdout
