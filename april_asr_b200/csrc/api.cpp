@@ -321,7 +321,7 @@ APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int res
     out->encoder_steps = s.encoder_steps; out->joiner_passes = s.joiner_passes; out->decoder_runs = s.decoder_runs; out->frames = s.frames;
     out->kernel_launches = s.kernel_launches; out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
     out->device_ms = s.device_ms; out->lstm_scan_ms = s.lstm_scan_ms; out->gemm_ms = s.gemm_ms;
-    out->compute_ms = s.compute_ms; out->gemm_flops = s.gemm_flops; out->gemm_launches = s.gemm_launches;
+    out->compute_ms = s.compute_ms; out->gemm_flops = s.gemm_flops; out->gemm_launches = s.gemm_launches; out->greedy_ms = s.greedy_ms;
     return 0;
 }
 

@@ -95,6 +95,19 @@ static CUtensorMap make_map_kblocks_hl(const void* ptr, uint64_t rows, uint64_t 
     return m;
 }
 
+// 3-D view of the gate pre-activations G [rows, 4H] fp32: {unit, gate, row}; one box = 8 units x 4 gates x box_rows rows
+static CUtensorMap make_map_g3(const void* ptr, uint64_t rows, uint64_t H, uint32_t box_units, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = { H, 4, rows };
+    cuuint64_t strides[2] = { H * sizeof(float), 4 * H * sizeof(float) };
+    cuuint32_t box[3] = { box_units, 4, box_rows };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (G 3-D) failed: %d\n", (int)r); abort(); }
+    return m;
+}
+
 // 5-D view of the scan2 exchange buffer Mx[t][hl][session][H]: {64-wide k-block element, session, hi|lo, k-block, time}
 static CUtensorMap make_map_mx(const void* ptr, uint64_t Bs, uint64_t H, uint64_t Trows, uint32_t box_sessions, uint32_t box_kb) {
     CUtensorMap m;
@@ -175,7 +188,7 @@ public:
     void span_begin(int cls) { if (!profile) return; Span sp{ ev_get(), ev_get(), cls }; CK(cudaEventRecord(sp.a, st)); spans.push_back(sp); }
     void span_end() { if (!profile) return; CK(cudaEventRecord(spans.back().b, st)); }
     void spans_collect() {
-        for (auto& sp : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, sp.a, sp.b)); (sp.cls == 0 ? stat.gemm_ms : stat.lstm_scan_ms) += ms; ev_pool.push_back(sp.a); ev_pool.push_back(sp.b); }
+        for (auto& sp : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, sp.a, sp.b)); (sp.cls == 0 ? stat.gemm_ms : (sp.cls == 1 ? stat.lstm_scan_ms : stat.greedy_ms)) += ms; ev_pool.push_back(sp.a); ev_pool.push_back(sp.b); }
         spans.clear();
     }
 
@@ -580,7 +593,7 @@ public:
         scan2 = (H % 64 == 0) && (H % scan2::UNITS == 0) && (H / scan2::UNITS <= num_sms) && (D % 8 == 0) && !(sel && !strcmp(sel, "v1")) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
         if (!scan2) return;
         const int KBH = H / 64, GC = H / scan2::UNITS;
-        scan2_smem = 1024 + (size_t)KBH * 8192 + (size_t)scan2::RSTAGES * 16384 + 64 * 65 * 4 + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + 512;
+        scan2_smem = 1024 + (size_t)KBH * 8192 + (size_t)scan2::RSTAGES * 16384 + 64 * 65 * 4 + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + scan2::MAXG * 64 * 4 + 2 * scan2::EPI_WARPS * 32 * 2 + 512;
         if (scan2_smem > 227 * 1024) { scan2 = false; return; }
         CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan2_smem));
         CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
@@ -641,14 +654,19 @@ public:
         for (int g0 = 0; g0 < B; g0 += 64) {
             const int Bc = std::min(64, B - g0);
             scan2::Scan2Args a{};
-            static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 2;
-            a.T = tc; a.t0 = t0; a.NG = (groups_env == 2 && Bc > 16) ? 2 : 1;
-            a.Bg[0] = a.NG == 2 ? (Bc + 1) / 2 : Bc; a.Bg[1] = Bc - a.Bg[0];
-            a.goff[0] = 0; a.goff[1] = a.Bg[0];
-            a.Bp = (a.Bg[0] + 15) & ~15;
+            static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 2;   // measured: every tcgen05.mma costs >= ~84 clk to issue whatever its N, so more (smaller) groups cost more issue time
+            a.T = tc; a.t0 = t0;
+            a.NG = std::max(1, std::min({ groups_env, (int)scan2::MAXG, (Bc + 15) / 16 }));       // interleaved groups of >= 16 sessions
+            const int per = (Bc + a.NG - 1) / a.NG;
+            for (int g = 0, o = 0; g < scan2::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::min(per, Bc - o) : 0; o += a.Bg[g]; }
+            a.Bp = (per + 15) & ~15;
             a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan2::UNITS;
             const int KBH = H / 64;
             a.KBG = 1; for (int kk = 1; kk <= KBH; kk++) if (KBH % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
+            static const bool m64_env = !(getenv("APRIL_B200_SCAN_M128"));
+            static const int dbg_env = getenv("APRIL_B200_SCAN_DBG") ? atoi(getenv("APRIL_B200_SCAN_DBG")) : 0;
+            a.dbg = dbg_env;
+            a.m64 = m64_env ? 1 : 0;
             a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.c_state = cw; a.m_state = mw;
             a.Mx = Mx; a.Mall_hi = b_mall_h.as<__half>(); a.Mall_lo = b_mall_l.as<__half>(); a.counter = scan_counters;
             static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
@@ -656,7 +674,7 @@ public:
             if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
             CK(cudaMemsetAsync(scan_counters, 0, 4 * sizeof(unsigned), st));
             CUtensorMap mMx = make_map_mx(Mx, (uint64_t)B, (uint64_t)H, (uint64_t)tc + 1, (uint32_t)a.Bp, (uint32_t)a.KBG);
-            CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, scan2::UNITS, (uint32_t)a.Bp, false);
+            CUtensorMap mG = make_map_g3(G, (uint64_t)tc * B, (uint64_t)H, scan2::UNITS, (uint32_t)a.Bp);
             {
                 cudaLaunchConfig_t cfg{};
                 cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan2::THREADS); cfg.dynamicSmemBytes = scan2_smem; cfg.stream = st;
@@ -1015,6 +1033,7 @@ public:
                 if (npass == 0) gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
                 else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
+                span_begin(2);
                 if (fast_greedy) {
                     const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
                     const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));
@@ -1026,6 +1045,7 @@ public:
                                                                  b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc);
                 }
                 launch_check();
+                span_end();
                 if (want_tap) { CK(cudaMemcpyAsync(p_eo.as<float>() + (size_t)t0 * B * J, EO, sizeof(float) * (size_t)M * J, cudaMemcpyDeviceToHost, st)); stat.d2h_bytes += sizeof(float) * (size_t)M * J; }
             }
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();

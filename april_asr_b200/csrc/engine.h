@@ -46,6 +46,7 @@ struct EngineStats {
     uint64_t encoder_steps = 0, joiner_passes = 0, decoder_runs = 0, frames = 0, kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     double device_ms = 0, lstm_scan_ms = 0, gemm_ms = 0, compute_ms = 0, gemm_flops = 0;
     uint64_t gemm_launches = 0;
+    double greedy_ms = 0;
 };
 
 typedef void (*TapFn)(void* userdata, void* cookie, int net, const float* data, size_t n);

@@ -31,13 +31,22 @@ using scan::red_release;
 using scan::wait_counter;
 using scan::epi_bar_sync;
 
-constexpr int THREADS = 320;               // warps 0-3: one TMA ring stage each (a spinning lane must not share a warp with another producer),
-                                          // warp 4: weights + G loader, warp 5: MMA issuer, warps 6-9: epilogue
 constexpr int UNITS = 8;                  // hidden units per CTA -> 32 gate rows, 64 stacked (hi ; lo)
 constexpr int RSTAGES = 4;                // activation ring stages
-constexpr int MAXG = 2;
-// Up to two independent session groups are interleaved through the CTA (as in kernels_scan.cuh): the ring keeps
-// streaming group 1's m rows while group 0 is in its epilogue / handover, and vice versa. An optional thread-block
+constexpr int MAXG = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int MMAW = 4;                   // MMA-issuing warps = accumulators per group
+// warps 0-3: one TMA ring stage each (a spinning lane must not share a warp with another producer), warp 4: weights + G loader,
+// warps 5-8: MMA issuers, warps 9-16: epilogue (TMEM drain + cell update), warps 17-20: one releaser per session group (the
+// store-acknowledge wait of the release is ~1.4 us: it must not hold the epilogue team, which serves the groups in turn).
+// Why four MMA warps: measured on B200 (probe_mma.cu), one thread issues a tcgen05.mma every >= ~84 clk whatever M and N
+// (N <= 128), so a group's H/16 = 64 K-slices cost 2.7 us from one thread. The limit is per issuing thread: four warps,
+// each owning K-slice (k mod 4) of every k-block and its own TMEM accumulator, issue concurrently (~24-32 clk apart).
+constexpr int THREADS = (RSTAGES + 1 + MMAW + EPI_WARPS + MAXG) * 32;
+// Up to MAXG independent session groups are interleaved through the CTA (as in kernels_scan.cuh): the ring keeps
+// streaming another group's m rows while one group is in its epilogue / handover. A group's step is a fixed chain
+// (TMA landing, MMA tail, drain, cell, release, poll: ~7 us measured) plus its own ingest, so small groups (16 sessions)
+// shorten the chain and more of them fill the ring. An optional thread-block
 // cluster (CS CTAs) fetches each copy once and multicasts it; measured on B200 this does not help (the ring, not L2,
 // bounds the ingest), so the default is CS = 1.
 
@@ -46,11 +55,13 @@ struct Scan2Args {
     int NG;                // interleaved groups
     int Bg[MAXG];          // sessions per group
     int goff[MAXG];        // first session of the group relative to g0
-    int Bp;                // padded group size (multiple of 16, <= 64 for NG = 1, <= 32 for NG = 2)
+    int Bp;                // padded group size (multiple of 16, NG * Bp <= 64)
     int Bs, g0;            // sessions in the whole pass = row stride of G / M buffers; first session of this launch
     int H;
     int GC;                // CTAs = H / 8
     int KBG;               // k-blocks per TMA copy
+    int m64;               // 1: UMMA M = 64 (no over-read of 64 unused rows; accumulator rows sit in lanes 0-15 of each TMEM quarter)
+    int dbg;               // timing experiments only (results are wrong): bit 0 = skip the UMMAs, bit 1 = skip the ring's TMA loads
     float inv_scale;
     const int* nsteps;     // [Bs] (not offset)
     float* c_state;        // [Bs, H] fp32 pass-layout state of this layer (read at start, written at end)
@@ -79,6 +90,15 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
 }
 __device__ __forceinline__ uint32_t cluster_ctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void epi2_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 __device__ __forceinline__ void cluster_sync_() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -87,7 +107,7 @@ __device__ __forceinline__ void cluster_sync_() {
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H] stacked W_eff slices, box {64, 64}
                   const __grid_constant__ CUtensorMap mapMx,   // 5-D {64, Bs, 2, H/64, T+1}, box {64, Bp, 2, KBG, 1}
-                  const __grid_constant__ CUtensorMap mapG,    // 2-D fp32 [T*Bs, 4H], box {8, Bp}
+                  const __grid_constant__ CUtensorMap mapG,    // 3-D fp32 view of [T*Bs, 4H]: {unit, gate, row}, box {8, 4, Bp}
                   Scan2Args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -95,6 +115,7 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
     auto gptr = [&](uint32_t saddr) { return base_ptr + (saddr - base); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NG = a.NG;
+    constexpr int NACC = MMAW;
 
     const int KB_W = a.H / 64;
     const uint32_t w_kb_bytes = 64u * 128u, WBYTES = (uint32_t)KB_W * w_kb_bytes;
@@ -107,7 +128,9 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
     const uint32_t GB = (uint32_t)a.Bp * UNITS * 4u * 4u;                 // 4 gates x [Bp x 8] fp32, per group
     const uint32_t cbuf = gbuf0 + (uint32_t)NG * GB;
     const uint32_t CB = (uint32_t)a.Bp * UNITS * 4u;                      // per group
-    const uint32_t bar0 = (cbuf + (uint32_t)NG * CB + 15u) & ~15u;
+    const uint32_t nbuf = cbuf + (uint32_t)NG * CB;                       // [MAXG][64] int: live steps per session
+    const uint32_t stg0 = nbuf + MAXG * 64 * 4;                           // [2][256] fp16 staging: 8 units of a session -> one 16-byte store
+    const uint32_t bar0 = (stg0 + 2u * EPI_WARPS * 32u * 2u + 15u) & ~15u;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (RSTAGES + s); };
     const uint32_t wfull_bar = bar0 + 8u * (2 * RSTAGES);
@@ -115,50 +138,60 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
     auto tempty_bar = [&](int g) { return wfull_bar + 8u + 8u * (MAXG + g); };
     auto gfull_bar = [&](int g) { return wfull_bar + 8u + 8u * (2 * MAXG + g); };
     auto gfree_bar = [&](int g) { return wfull_bar + 8u + 8u * (3 * MAXG + g); };
-    const uint32_t tmem_slot = wfull_bar + 8u + 8u * (4 * MAXG);
+    auto rel_bar = [&](int g) { return wfull_bar + 8u + 8u * (4 * MAXG + g); };
+    const uint32_t tmem_slot = wfull_bar + 8u + 8u * (5 * MAXG);
     float* exch = reinterpret_cast<float*>(gptr(exch0));
     float* cst = reinterpret_cast<float*>(gptr(cbuf));
 
     const uint32_t crank = cluster_ctarank_(), CS = cluster_nctarank_();
     const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < RSTAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CS); }
+        for (int s = 0; s < RSTAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MMAW * CS); }
         mbar_init(wfull_bar, 1);
-        for (int g = 0; g < MAXG; g++) { mbar_init(tfull_bar(g), 1); mbar_init(tempty_bar(g), 1); mbar_init(gfull_bar(g), 1); mbar_init(gfree_bar(g), 1); }
+        for (int g = 0; g < MAXG; g++) { mbar_init(tfull_bar(g), MMAW); mbar_init(tempty_bar(g), 1); mbar_init(gfull_bar(g), 1); mbar_init(gfree_bar(g), 1); mbar_init(rel_bar(g), 1); }
         fence_barrier_init();
     }
-    const uint32_t tmem_cols = (uint32_t)(NG * Nact) <= 32u ? 32u : ((uint32_t)(NG * Nact) <= 64u ? 64u : 128u);
+    uint32_t tmem_cols = 32; while (tmem_cols < (uint32_t)(NG * NACC * Nact)) tmem_cols <<= 1;
     if (warp == RSTAGES + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     if (CS > 1) cluster_sync_();                                          // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(gptr(tmem_slot));
-    const uint32_t idesc = make_idesc_f16(128, Nact);
+    const uint32_t idesc = make_idesc_f16(a.m64 ? 64 : 128, Nact);
     const int u0 = blockIdx.x * UNITS;
     const int copies = KB_W / a.KBG;                                      // TMA copies per (step, group)
 
     if (warp < RSTAGES) {
-        if (lane == 0) {
-            const int stage = warp;
-            tma_prefetch_desc(&mapMx);
-            const long long total = (long long)a.T * NG * copies;
-            int opened_t = -1, opened_g = -1;
-            for (long long idx = stage; idx < total; idx += RSTAGES) {
-                const int j = (int)(idx % copies);
-                const int tg = (int)(idx / copies), g = tg % NG, t = tg / NG;
-                if (t != opened_t || g != opened_g) {
-                    if (t > 0) wait_counter(a.counter + g, (unsigned)t * (unsigned)a.GC);     // m(t-1) of the group complete everywhere
-                    opened_t = t; opened_g = g;
-                    if (j == 0) TRACE2(0);
+        // convergent warp; lane 0 polls the handover counter, one elected lane issues the copy
+        const int stage = warp;
+        if (lane == 0) tma_prefetch_desc(&mapMx);
+        const long long total = (long long)a.T * NG * copies;
+        int opened_t = -1, opened_g = -1;
+        for (long long idx = stage; idx < total; idx += RSTAGES) {
+            const int j = (int)(idx % copies);
+            const int tg = (int)(idx / copies), g = tg % NG, t = tg / NG;
+            if (t != opened_t || g != opened_g) {
+                if (t > 0) {
+                    if (lane == 0) wait_counter(a.counter + g, (unsigned)t * (unsigned)a.GC);     // m(t-1) of the group complete everywhere
+                    __syncwarp();
+                    asm volatile("fence.proxy.async;" ::: "memory");     // whichever lane is elected below issues its TMA read after the acquire
                 }
-                const uint32_t use = (uint32_t)(idx / RSTAGES);
-                mbar_wait(empty_bar(stage), (use & 1) ^ 1);              // stage free (in every CTA of the cluster)
-                mbar_expect_tx(full_bar(stage), SB);
-                if (CS == 1) tma_load_5d(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t);   // row t holds m(t-1)
-                else if ((uint32_t)j % CS == crank) tma_load_5d_mc(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t, cmask);
-                if (j == copies - 1) TRACE2(1);
+                opened_t = t; opened_g = g;
+                if (j == 0 && lane == 0) TRACE2(0);
             }
+            const uint32_t use = (uint32_t)(idx / RSTAGES);
+            mbar_wait(empty_bar(stage), (use & 1) ^ 1);                  // stage free (in every CTA of the cluster)
+            if (elect_one()) {
+                if (a.dbg & 2) mbar_arrive(full_bar(stage));
+                else {
+                    mbar_expect_tx(full_bar(stage), SB);
+                    if (CS == 1) tma_load_5d(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t);   // row t holds m(t-1)
+                    else if ((uint32_t)j % CS == crank) tma_load_5d_mc(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t, cmask);
+                }
+            }
+            __syncwarp();
+            if (j == copies - 1 && lane == 0) TRACE2(1);
         }
     } else if (warp == RSTAGES) {
         if (lane == 0) {
@@ -169,125 +202,129 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
                 for (int g = 0; g < NG; g++) {
                     if (t > 0) mbar_wait(gfree_bar(g), (t - 1) & 1);
                     mbar_expect_tx(gfull_bar(g), GB);
-                    for (int g4 = 0; g4 < 4; g4++) tma_load_2d(gbuf0 + g * GB + g4 * (GB / 4), &mapG, gfull_bar(g), g4 * a.H + u0, t * a.Bs + a.g0 + a.goff[g]);
+                    tma_load_3d(gbuf0 + g * GB, &mapG, gfull_bar(g), u0, 0, t * a.Bs + a.g0 + a.goff[g]);          // lands as [session][gate][8 units]
                 }
         }
-    } else if (warp == RSTAGES + 1) {
-        if (lane == 0) {
-            mbar_wait(wfull_bar, 0);
-            long long idx = 0;
-            for (int t = 0; t < a.T; t++)
-                for (int g = 0; g < NG; g++) {
-                    mbar_wait(tempty_bar(g), (t & 1) ^ 1);
+    } else if (warp < RSTAGES + 1 + MMAW) {
+        // MMA warp mw issues K-slice mw of every k-block into its own accumulator. The whole warp walks the loop
+        // (convergent, so descriptors live in uniform registers); one elected lane issues the tcgen05 instructions.
+        const int mw = warp - (RSTAGES + 1);
+        mbar_wait(wfull_bar, 0);
+        long long idx = 0;
+        for (int t = 0; t < a.T; t++)
+            for (int g = 0; g < NG; g++) {
+                mbar_wait(tempty_bar(g), (t & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (g * NACC + mw) * Nact;
+                for (int j = 0; j < copies; j++, idx++) {
+                    const int s = (int)(idx % RSTAGES);
+                    const uint32_t use = (uint32_t)(idx / RSTAGES);
+                    mbar_wait(full_bar(s), use & 1);
+                    if (j == 0 && mw == 0 && lane == 0) TRACE2(2);
                     tc_fence_after();
-                    for (int j = 0; j < copies; j++, idx++) {
-                        const int s = (int)(idx % RSTAGES);
-                        const uint32_t use = (uint32_t)(idx / RSTAGES);
-                        mbar_wait(full_bar(s), use & 1);
-                        if (j == 0) TRACE2(2);
-                        tc_fence_after();
-                        for (int kk = 0; kk < a.KBG; kk++) {
-                            const uint64_t ad = make_sw128_desc(base + (j * a.KBG + kk) * w_kb_bytes), bd = make_sw128_desc(ring0 + s * SB + kk * KBB);
-#pragma unroll
-                            for (int k = 0; k < 4; k++) umma_f16(tmem_base + g * Nact, ad + 2 * k, bd + 2 * k, idesc, (j | kk | k) != 0);
-                        }
+                    if (elect_one()) {
+                        if (!(a.dbg & 1))
+                            for (int kk = 0; kk < a.KBG; kk++) {
+                                const uint64_t ad = make_sw128_desc(base + (j * a.KBG + kk) * w_kb_bytes), bd = make_sw128_desc(ring0 + s * SB + kk * KBB);
+                                umma_f16(d_tmem, ad + 2 * mw, bd + 2 * mw, idesc, (j | kk) != 0);
+                            }
                         if (CS == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
                     }
-                    umma_commit(tfull_bar(g));
-                    TRACE2(3);
+                    __syncwarp();
                 }
-        }
-    } else {
-        const int q = warp & 3, et = (warp - (RSTAGES + 2)) * 32 + lane;   // et: 0..127
-        // cell phase: Bp <= 32: session b = et / 4, units uq*2, uq*2+1 ; Bp == 64 (NG == 1): session b = et / 2, units uq*4 .. +3
-        const bool wide = a.Bp > 32;
-        const int upt = wide ? 4 : 2;                                      // units per thread
-        const int my_b = wide ? (et >> 1) : (et >> 2), uq = wide ? (et & 1) : (et & 3);
-        int my_n[MAXG];
-        for (int g = 0; g < MAXG; g++) {
-            const int sess = a.g0 + (g < NG ? a.goff[g] : 0) + my_b;
-            my_n[g] = (g < NG && my_b < a.Bg[g]) ? a.nsteps[sess] : 0;
-            if (g < NG && my_b < a.Bp)
-                for (int uu = 0; uu < upt; uu++)
-                    cst[g * (a.Bp * UNITS) + my_b * UNITS + uq * upt + uu] = my_b < a.Bg[g] ? a.c_state[(size_t)sess * a.H + u0 + uq * upt + uu] : 0.f;
-        }
+                if (elect_one()) umma_commit(tfull_bar(g));
+                __syncwarp();
+                if (mw == 0 && lane == 0) TRACE2(3);
+            }
+    } else if (warp < RSTAGES + 1 + MMAW + EPI_WARPS) {
+        const int ew = warp - (RSTAGES + 1 + MMAW), et = ew * 32 + lane;         // et: 0..255
+        const int q = warp & 3, half = ew >> 2;                           // TMEM lane quarter of this warp; the two warps of a quarter split the columns
+        const int cells = a.Bp * UNITS;                                   // (session, unit) pairs of a group: cell idx = b * 8 + u, thread et owns idx = et (+256)
+        int* sn = reinterpret_cast<int*>(gptr(nbuf));
+        __half* stg_h = reinterpret_cast<__half*>(gptr(stg0));
+        __half* stg_l = stg_h + EPI_WARPS * 32;
+        for (int g = 0; g < NG; g++)
+            for (int idx = et; idx < cells; idx += EPI_WARPS * 32) {
+                const int b = idx >> 3, u = idx & 7, sess = a.g0 + a.goff[g] + b;
+                cst[g * cells + idx] = b < a.Bg[g] ? a.c_state[(size_t)sess * a.H + u0 + u] : 0.f;
+                if (u == 0) sn[g * 64 + b] = b < a.Bg[g] ? a.nsteps[sess] : 0;
+            }
+        epi2_bar_sync();
         for (int t = 0; t < a.T; t++)
             for (int g = 0; g < NG; g++) {
                 mbar_wait(tfull_bar(g), t & 1);
                 if (et == 0) TRACE2(4);
                 tc_fence_after();
-                if (q < 2) {                                              // TMEM lanes 0-31: W_hi rows, 32-63: W_lo rows
-                    const uint32_t tb = tmem_base + g * Nact + ((uint32_t)(q * 32) << 16);
-                    if (a.Bp == 16) {
-                        float v[32];
-                        tmem_ld32(tb, v);
+                if (a.m64 || q < 2) {                                     // rows 0-31: W_hi, 32-63: W_lo; columns [0,Bp): m_hi, [Bp,2Bp): m_lo
+                    // M = 128: row r in lane r (quarters 0, 1). M = 64: row r in lane 32 * (r / 16) + r % 16 (16 rows per quarter)
+                    const uint32_t tb = tmem_base + g * NACC * Nact + ((uint32_t)(q * 32) << 16);
+                    const int row = a.m64 ? q * 16 + lane : q * 32 + lane;
+                    const bool valid = !a.m64 || lane < 16;
+                    const int nc = a.Bp >> 1, c0 = half * nc;
+                    for (int c = c0; c < c0 + nc; c += 8) {
+                        uint32_t v[4][8], w2[4][8];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) exch[(q * 32 + lane) * ld + j] = v[j] + v[16 + j];
-                    } else {
-                        for (int c0 = 0; c0 < a.Bp; c0 += 32) {
-                            float v[32], w2[32];
-                            tmem_ld32(tb + c0, v);
-                            tmem_ld32(tb + a.Bp + c0, w2);
+                        for (int ac = 0; ac < 4; ac++)
+                            if (ac < NACC) { tmem_ld8_nowait(tb + ac * Nact + c, v[ac]); tmem_ld8_nowait(tb + ac * Nact + a.Bp + c, w2[ac]); }
+                        tc_wait_ld();
+                        if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) if (c0 + j < a.Bp) exch[(q * 32 + lane) * ld + c0 + j] = v[j] + w2[j];
+                            for (int j = 0; j < 8; j++) {
+                                float sum = __uint_as_float(v[0][j]) + __uint_as_float(w2[0][j]);
+#pragma unroll
+                                for (int ac = 1; ac < 4; ac++) if (ac < NACC) sum += __uint_as_float(v[ac][j]) + __uint_as_float(w2[ac][j]);
+                                exch[row * ld + c + j] = sum;
+                            }
                         }
                     }
                 }
                 tc_fence_before();
-                epi_bar_sync();
+                epi2_bar_sync();
                 if (et == 0) { mbar_arrive(tempty_bar(g)); TRACE2(5); }
                 mbar_wait(gfull_bar(g), t & 1);
-                if (my_b < a.Bp) {
-                    const float* gb = reinterpret_cast<const float*>(gptr(gbuf0 + g * GB));
-                    float* cs = cst + g * (a.Bp * UNITS) + my_b * UNITS + uq * upt;
-                    const bool live = a.t0 + t < my_n[g];
-                    const int sess = a.g0 + a.goff[g] + my_b;
-                    float mval[4];
+                const float* gb = reinterpret_cast<const float*>(gptr(gbuf0 + g * GB));
+                for (int idx = et; idx < cells; idx += EPI_WARPS * 32) {  // warp-uniform trip count (cells is a multiple of 128)
+                    const int b = idx >> 3, u = idx & 7;
+                    const int n_live = sn[g * 64 + b];
+                    const bool live = a.t0 + t < n_live;                  // ragged: finished / padding sessions keep their state
+                    const int sess = a.g0 + a.goff[g] + b;
+                    float gate[4];
 #pragma unroll
-                    for (int uu = 0; uu < 4; uu++) {
-                        if (uu < upt) {
-                            const int u = uq * upt + uu;
-                            float gate[4];
-#pragma unroll
-                            for (int g4 = 0; g4 < 4; g4++)
-                                gate[g4] = (exch[(g4 * 8 + u) * ld + my_b] + exch[(32 + g4 * 8 + u) * ld + my_b]) * a.inv_scale + gb[(g4 * a.Bp + my_b) * UNITS + u];
-                            const float cn = fast_sigmoid(gate[1]) * cs[uu] + fast_sigmoid(gate[0]) * fast_tanh(gate[2]);
-                            if (live) cs[uu] = cn;
-                            mval[uu] = fast_sigmoid(gate[3]) * fast_tanh(cn);
-                        }
+                    for (int g4 = 0; g4 < 4; g4++)
+                        gate[g4] = (exch[(g4 * 8 + u) * ld + b] + exch[(32 + g4 * 8 + u) * ld + b]) * a.inv_scale + gb[(b * 4 + g4) * UNITS + u];
+                    const float cn = fast_sigmoid(gate[1]) * cst[g * cells + idx] + fast_sigmoid(gate[0]) * fast_tanh(gate[2]);
+                    const float mval = fast_sigmoid(gate[3]) * fast_tanh(cn);
+                    if (live) cst[g * cells + idx] = cn;
+                    __half mh, ml;
+                    split_f16(mval, mh, ml);
+                    stg_h[et] = mh; stg_l[et] = ml;
+                    if (live && ((a.t0 + t == n_live - 1) || (t == a.T - 1))) a.m_state[(size_t)sess * a.H + u0 + u] = mval;
+                    __syncwarp();
+                    if (live && u < 4) {                                  // lanes 8k..8k+7 hold one session: four of them store its 16-byte rows
+                        const uint4 val = *reinterpret_cast<const uint4*>((u & 1) ? (stg_l + (et - u)) : (stg_h + (et - u)));
+                        __half* dst = (u < 2) ? a.Mx + ((size_t)(t + 1) * 2 + u) * a.Bs * a.H + (size_t)sess * a.H
+                                              : ((u == 2) ? a.Mall_hi : a.Mall_lo) + ((size_t)t * a.Bs + sess) * a.H;
+                        *reinterpret_cast<uint4*>(dst + u0) = val;
                     }
-                    if (live) {
-                        __align__(8) __half mh[4], ml[4];
-#pragma unroll
-                        for (int uu = 0; uu < 4; uu++) if (uu < upt) split_f16(mval[uu], mh[uu], ml[uu]);
-                        const size_t col = (size_t)u0 + uq * upt;
-                        __half* mx = a.Mx + (size_t)(t + 1) * 2 * a.Bs * a.H;
-                        const size_t row = (size_t)t * a.Bs + sess;
-                        const bool endw = (a.t0 + t == my_n[g] - 1) || (t == a.T - 1);
-                        if (wide) {
-                            *reinterpret_cast<uint2*>(mx + (size_t)sess * a.H + col) = *reinterpret_cast<const uint2*>(mh);
-                            *reinterpret_cast<uint2*>(mx + ((size_t)a.Bs + sess) * a.H + col) = *reinterpret_cast<const uint2*>(ml);
-                            *reinterpret_cast<uint2*>(a.Mall_hi + row * a.H + col) = *reinterpret_cast<const uint2*>(mh);
-                            *reinterpret_cast<uint2*>(a.Mall_lo + row * a.H + col) = *reinterpret_cast<const uint2*>(ml);
-                            if (endw) *reinterpret_cast<float4*>(a.m_state + (size_t)sess * a.H + col) = make_float4(mval[0], mval[1], mval[2], mval[3]);
-                        } else {
-                            *reinterpret_cast<uint32_t*>(mx + (size_t)sess * a.H + col) = *reinterpret_cast<const uint32_t*>(mh);
-                            *reinterpret_cast<uint32_t*>(mx + ((size_t)a.Bs + sess) * a.H + col) = *reinterpret_cast<const uint32_t*>(ml);
-                            *reinterpret_cast<uint32_t*>(a.Mall_hi + row * a.H + col) = *reinterpret_cast<const uint32_t*>(mh);
-                            *reinterpret_cast<uint32_t*>(a.Mall_lo + row * a.H + col) = *reinterpret_cast<const uint32_t*>(ml);
-                            if (endw) *reinterpret_cast<float2*>(a.m_state + (size_t)sess * a.H + col) = make_float2(mval[0], mval[1]);
-                        }
-                    }
+                    __syncwarp();
                 }
-                if (et == 0) TRACE2(6);
-                asm volatile("fence.proxy.async;" ::: "memory");
-                epi_bar_sync();
-                if (et == 0) { red_release(a.counter + g); mbar_arrive(gfree_bar(g)); TRACE2(7); }
+                epi2_bar_sync();                                          // every store of this (step, group) is issued; exch / G buffer reusable
+                if (et == 0) { mbar_arrive(rel_bar(g)); mbar_arrive(gfree_bar(g)); TRACE2(6); }
             }
         for (int g = 0; g < NG; g++)
-            if (my_b < a.Bg[g]) {
-                const int sess = a.g0 + a.goff[g] + my_b;
-                for (int uu = 0; uu < upt; uu++) a.c_state[(size_t)sess * a.H + u0 + uq * upt + uu] = cst[g * (a.Bp * UNITS) + my_b * UNITS + uq * upt + uu];
+            for (int idx = et; idx < cells; idx += EPI_WARPS * 32) {
+                const int b = idx >> 3, u = idx & 7;
+                if (b < a.Bg[g]) a.c_state[(size_t)(a.g0 + a.goff[g] + b) * a.H + u0 + u] = cst[g * cells + idx];
+            }
+    } else {
+        // releaser of group g: CTA-scope ordering came through the mbarrier; the gpu-scope release is cumulative over it
+        const int g = warp - (RSTAGES + 1 + MMAW + EPI_WARPS);
+        if (g < NG && lane == 0)
+            for (int t = 0; t < a.T; t++) {
+                mbar_wait(rel_bar(g), t & 1);
+                asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores -> the peers' TMA (async proxy) reads
+                red_release(a.counter + g);
+                TRACE2(7);
             }
     }
     tc_fence_before();

@@ -728,14 +728,27 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
                         e_pf[s][u] = (s < ns && j < J && t + 1 < s_n[s]) ? enc_out[((size_t)(t + 1 - t_base) * B + s0 + s) * J + j] : 0.f;
                     }
             }
-            for (int s = 0; s < ns; s++) {
-                if (s_done[s]) continue;
+            // all sessions' table rows are requested before any is used: one DRAM round trip per pass, not one per session
+            float d_new[GC_MAX_S][2];
+#pragma unroll
+            for (int s = 0; s < GC_MAX_S; s++) {
+                const bool nc = s < ns && !s_done[s] && s_newctx[s] != 0;
+                const float* drow = nc ? dtab + ((size_t)st[s].ctx0 * V + st[s].ctx1) * J : dtab;
+#pragma unroll
+                for (int u = 0; u < 2; u++) { const int j = threadIdx.x + u * 256; d_new[s][u] = (nc && j < J) ? __ldg(drow + j) : 0.f; }
+            }
+#pragma unroll
+            for (int s = 0; s < GC_MAX_S; s++) {
+                if (s >= ns || s_done[s]) continue;
                 const bool nc = s_newctx[s] != 0;
-                const float* drow = dtab + ((size_t)st[s].ctx0 * V + st[s].ctx1) * J;
-                for (int j = threadIdx.x; j < J; j += blockDim.x) {
-                    float dv;
-                    if (nc) { dv = drow[j]; ds[(size_t)s * J + j] = dv; } else dv = ds[(size_t)s * J + j];
-                    zs[(size_t)s * J + j] = tanhf(e_cur[(size_t)s * J + j] + dv);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = threadIdx.x + u * 256;
+                    if (j < J) {
+                        float dv;
+                        if (nc) { dv = d_new[s][u]; ds[(size_t)s * J + j] = dv; } else dv = ds[(size_t)s * J + j];
+                        zs[(size_t)s * J + j] = tanhf(e_cur[(size_t)s * J + j] + dv);
+                    }
                 }
             }
             __syncthreads();

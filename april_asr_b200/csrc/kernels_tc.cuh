@@ -76,6 +76,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrives on the mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+// true in exactly one lane of a fully converged warp. The warp stays convergent around the single-thread tcgen05
+// instructions, so their descriptor operands are computed warp-uniformly (uniform registers, no per-lane waterfall loop).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -179,10 +186,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
-            if (NPASS == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
+        // ===================== TMA producer: convergent warp, one elected lane issues =====================
+        {
+            if (lane == 0) {
+                tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
+                if (NPASS == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
+            }
+            __syncwarp();
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
@@ -190,19 +200,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     const int s = it % S; const uint32_t ph = (it / S) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-                    tma_load_2d(st, &mapAhi, full_bar(s), kb * GEMM_BK, m0);
-                    tma_load_2d(st + Cfg::A_BYTES, &mapBhi, full_bar(s), kb * GEMM_BK, n0);
-                    if (NPASS == 3) {
-                        tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mapAlo, full_bar(s), kb * GEMM_BK, m0);
-                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, full_bar(s), kb * GEMM_BK, n0);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                        tma_load_2d(st, &mapAhi, full_bar(s), kb * GEMM_BK, m0);
+                        tma_load_2d(st + Cfg::A_BYTES, &mapBhi, full_bar(s), kb * GEMM_BK, n0);
+                        if (NPASS == 3) {
+                            tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mapAlo, full_bar(s), kb * GEMM_BK, m0);
+                            tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, full_bar(s), kb * GEMM_BK, n0);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: convergent warp, one elected lane issues =====================
+        {
             constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, GEMM_BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
@@ -216,21 +229,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     tc_fence_after();
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     const uint64_t ahi = make_sw128_desc(st), bhi = make_sw128_desc(st + Cfg::A_BYTES);
-                    if (NPASS == 3) {
-                        const uint64_t alo = make_sw128_desc(st + Cfg::A_BYTES + Cfg::B_BYTES), blo = make_sw128_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    const uint64_t alo = make_sw128_desc(st + Cfg::A_BYTES + Cfg::B_BYTES), blo = make_sw128_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    const uint32_t first = kb != 0;
+                    if (elect_one()) {
+                        if (NPASS == 3) {
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, first || k != 0);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, 1);
+                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
-                    } else {
+                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, first || k != 0);
+                        }
+                        umma_commit(empty_bar(s));         // smem stage free once these MMAs have read it
                     }
-                    umma_commit(empty_bar(s));             // smem stage free once these MMAs have read it
+                    __syncwarp();
                 }
-                umma_commit(tfull_bar(acc));               // accumulator complete
+                if (elect_one()) umma_commit(tfull_bar(acc));   // accumulator complete
+                __syncwarp();
             }
         }
     } else {

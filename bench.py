@@ -286,7 +286,7 @@ def main():
                          "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                          "traffic": 838.8e6, "traffic_note": "dram bytes read+written by one W_ih launch (M=49664,N=4096,K=512), ncu --set full, profiles/r01_ncu_raw_gemm.csv; algorithmic bytes of that launch: 923e6",
                          "precision": "fp16x3 split (3 tensor-core MMAs per algorithmic product; tokens identical to the fp32 reference); algorithmic FLOPs counted once",
-                         "gemm_ms_per_step": st.gemm_ms / a.steps, "lstm_scan_ms_per_step": st.lstm_scan_ms / a.steps,
+                         "gemm_ms_per_step": st.gemm_ms / a.steps, "greedy_ms_per_step": st.greedy_ms / a.steps, "lstm_scan_ms_per_step": st.lstm_scan_ms / a.steps,
                          "whole_pass_tflops": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12,
                          "lstm_scan": {"bound": "latency", "us_per_layer_step": 1e3 * st.lstm_scan_ms / max(1.0, (st.encoder_steps / S) * 12), "algorithmic_tflops": (st.encoder_steps * 2.0 * 31_457_280) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e12},
                          "whole_pass_frac": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12 / peak_tf},

@@ -53,6 +53,7 @@ typedef struct AprilB200Stats {
     double   compute_ms;        /* device_ms minus the host->device upload at the head of each pass */
     double   gemm_flops;        /* algorithmic FLOPs (2 M N K) of the GEMM launches timed in gemm_ms */
     uint64_t gemm_launches;
+    double   greedy_ms;         /* ... of which the joiner + greedy search kernel */
 } AprilB200Stats;
 
 /* Cumulative statistics of a model's engine; reset != 0 zeroes them after reading. lstm_scan_ms / gemm_ms /
