@@ -13,6 +13,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_scan.cuh"
 #include "kernels_scan2.cuh"
+#include "kernels_scan3.cuh"
 
 namespace april {
 
@@ -214,6 +215,8 @@ public:
     bool scan2 = false;
     size_t scan2_smem = 0;
     int scan2_cs = 1;               // thread-block cluster size of the scan (TMA multicast factor)
+    bool scan3 = false;             // K split over CTA pairs (kernels_scan3.cuh): same buffers and state as scan2, different W slicing
+    size_t scan3_smem = 0;
     float* m_store = nullptr;       // [slot][L][H]
     DevBuf b_mx, b_mall_h, b_mall_l, b_mw;
     __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
@@ -596,6 +599,15 @@ public:
         scan2_smem = 1024 + (size_t)KBH * 8192 + (size_t)scan2::RSTAGES * 16384 + 64 * 65 * 4 + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + scan2::MAXG * 64 * 4 + 2 * scan2::EPI_WARPS * 32 * 2 + 512;
         if (scan2_smem > 227 * 1024) { scan2 = false; return; }
         CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan2_smem));
+        scan3_smem = 1024 + (size_t)(H / 128) * 16384 + (size_t)scan2::RSTAGES * 16384 + scan3::TEAMS * (64 * 33 * 4 + 64 * 36 * 4) + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + scan2::MAXG * 64 * 4 + scan3::TEAMS * 2 * scan2::EPI_WARPS * 32 * 2 + 512;   // groups of <= 32 sessions
+        scan3 = (H % 128 == 0) && scan3_smem <= 227 * 1024 && !(sel && !strcmp(sel, "v2"));
+        if (scan3) {
+            CK(cudaFuncSetAttribute(scan3::lstm_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan3_smem));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan3::THREADS3); cfg.dynamicSmemBytes = scan3_smem; cfg.stream = st;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, scan3::lstm_scan3_kernel, &cfg) != cudaSuccess || ncl * 2 < GC) { cudaGetLastError(); scan3 = false; }   // all pairs must be co-resident
+        }
         CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
         CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
         float *dA = nullptr, *dB = nullptr, *dC = nullptr;
@@ -611,6 +623,22 @@ public:
             CK(cudaStreamSynchronize(st));
             const float sc = pow2_scale(weff, sl.inv);
             std::vector<__half> wg((size_t)GC * 64 * H);
+            if (scan3) {
+                // CTA c = pair * 2 + r: 128 stacked rows rho = hl * 64 + half * 32 + gate * 8 + u of units pair * 16 + half * 8 + u, K half r
+                const int KH = H / 2;
+                for (int c = 0; c < GC; c++)
+                    for (int rho = 0; rho < 128; rho++) {
+                        const int hl = rho >> 6, half = (rho >> 5) & 1, g4 = (rho >> 3) & 3, u = rho & 7, r = c & 1, pair = c >> 1;
+                        const float* src = weff.data() + ((size_t)g4 * H + (size_t)pair * 16 + half * 8 + u) * H + (size_t)r * KH;
+                        __half* dst = wg.data() + ((size_t)c * 128 + rho) * KH;
+                        for (int k = 0; k < KH; k++) {
+                            const float x = src[k] * sc; const __half hh = __float2half_rn(x);
+                            dst[k] = hl ? __float2half_rn(x - __half2float(hh)) : hh;
+                        }
+                    }
+                sl.w = upload(wg);
+                sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 128, (uint64_t)KH, 64, 128, true);
+            } else {
             for (int c = 0; c < GC; c++)
                 for (int g4 = 0; g4 < 4; g4++)
                     for (int u = 0; u < scan2::UNITS; u++) {
@@ -621,6 +649,7 @@ public:
                     }
             sl.w = upload(wg);
             sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 64, (uint64_t)H, 64, 64, true);
+            }
             sl.w_hr = make_tc_weight(lw.w_hr, D, H);
             s2layers.push_back(sl);
         }
@@ -657,12 +686,15 @@ public:
             static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 2;   // measured: every tcgen05.mma costs >= ~84 clk to issue whatever its N, so more (smaller) groups cost more issue time
             a.T = tc; a.t0 = t0;
             a.NG = std::max(1, std::min({ groups_env, (int)scan2::MAXG, (Bc + 15) / 16 }));       // interleaved groups of >= 16 sessions
+            if (scan3) a.NG = std::max(a.NG, (Bc + 31) / 32);                                      // its exchange blocks hold <= 32 sessions per group
+            if (!scan3 && a.NG == 3) a.NG = Bc > 48 ? 4 : 2;                                                 // NG * Bp must stay <= 64
             const int per = (Bc + a.NG - 1) / a.NG;
             for (int g = 0, o = 0; g < scan2::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::min(per, Bc - o) : 0; o += a.Bg[g]; }
             a.Bp = (per + 15) & ~15;
             a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan2::UNITS;
             const int KBH = H / 64;
-            a.KBG = 1; for (int kk = 1; kk <= KBH; kk++) if (KBH % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
+            const int KBW = scan3 ? KBH / 2 : KBH;                                                 // k-blocks a CTA walks per step
+            a.KBG = 1; for (int kk = 1; kk <= KBW; kk++) if (KBW % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
             static const bool m64_env = !(getenv("APRIL_B200_SCAN_M128"));
             static const int dbg_env = getenv("APRIL_B200_SCAN_DBG") ? atoi(getenv("APRIL_B200_SCAN_DBG")) : 0;
             a.dbg = dbg_env;
@@ -682,7 +714,8 @@ public:
                 at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
                 at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = (unsigned)scan2_cs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 2;
-                CK(cudaLaunchKernelEx(&cfg, scan2::lstm_scan2_kernel, sl.mapW, mMx, mG, a));
+                if (scan3) { cfg.blockDim = dim3(scan3::THREADS3); cfg.dynamicSmemBytes = scan3_smem; cfg.numAttrs = 1; CK(cudaLaunchKernelEx(&cfg, scan3::lstm_scan3_kernel, sl.mapW, mMx, mG, a)); }   // cluster dims are compiled in
+                else CK(cudaLaunchKernelEx(&cfg, scan2::lstm_scan2_kernel, sl.mapW, mMx, mG, a));
             }
             launch_check();
             if (do_trace) dump_trace(a.GC, tc, a.GC / 2);

@@ -752,7 +752,9 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
                 }
             }
             __syncthreads();
-            if (threadIdx.x < ns) s_newctx[threadIdx.x] = 0;
+            // only a session that took part in this pass has consumed its flag: one that finished the step on a blank which ALSO
+            // reset its context (2.2 s of silence, april_session.c:411-416) keeps the flag for its next step while its cluster mates run on
+            if (threadIdx.x < ns && !s_done[threadIdx.x]) s_newctx[threadIdx.x] = 0;
             // --- B: logits of my rows: registers x shared z, 4 sessions per round
             for (int sg = 0; sg < ns; sg += GC_SG) {
                 float acc[32];
