@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
@@ -215,6 +216,7 @@ public:
     bool scan2 = false;
     size_t scan2_smem = 0;
     int scan2_cs = 1;               // thread-block cluster size of the scan (TMA multicast factor)
+    bool gemm_attr[16] = {};
     bool scan3 = false;             // K split over CTA pairs (kernels_scan3.cuh): same buffers and state as scan2, different W slicing
     size_t scan3_smem = 0;
     float* m_store = nullptr;       // [slot][L][H]
@@ -608,8 +610,6 @@ public:
             int ncl = 0;
             if (cudaOccupancyMaxActiveClusters(&ncl, scan3::lstm_scan3_kernel, &cfg) != cudaSuccess || ncl * 2 < GC) { cudaGetLastError(); scan3 = false; }   // all pairs must be co-resident
         }
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
         float *dA = nullptr, *dB = nullptr, *dC = nullptr;
         CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
         std::vector<float> weff((size_t)4 * H * H);
@@ -762,37 +762,43 @@ public:
         }
     }
 
-    void set_gemm_attrs() {
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<3, tc::GE_DSWISH_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<3>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<1, tc::GE_DSWISH_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<1>::SMEM_BYTES));
+    template <int NP, int EPI, int CL> void gemm_tc_launch(unsigned grid, const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, const tc::GemmArgs& g) {
+        bool& attr_done = gemm_attr[(NP == 3 ? 8 : 0) + EPI * 2 + (CL - 1)];   // per engine (= per device) and instantiation
+        if (!attr_done) { CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<NP, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<NP, CL>::SMEM_BYTES)); attr_done = true; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::GEMM_THREADS); cfg.dynamicSmemBytes = tc::GemmCfg<NP, CL>::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel<NP, EPI, CL>, mAh, mAl, mBh, mBl, g));
     }
+    template <int NP, int CL> void gemm_tc_epi(int epi, unsigned grid, const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, const tc::GemmArgs& g) {
+        if (epi == tc::GE_F32) gemm_tc_launch<NP, tc::GE_F32, CL>(grid, mAh, mAl, mBh, mBl, g);
+        else if (epi == tc::GE_F32_RESIDUAL) gemm_tc_launch<NP, tc::GE_F32_RESIDUAL, CL>(grid, mAh, mAl, mBh, mBl, g);
+        else if (epi == tc::GE_F32_RESIDUAL_SPLIT) gemm_tc_launch<NP, tc::GE_F32_RESIDUAL_SPLIT, CL>(grid, mAh, mAl, mBh, mBl, g);
+        else gemm_tc_launch<NP, tc::GE_DSWISH_SPLIT, CL>(grid, mAh, mAl, mBh, mBl, g);
+    }
+    void set_gemm_attrs() {}
 
     // C = A * W^T (+bias, epilogue) on the tensor cores. A given as fp16 (hi, lo) [M, K].
     void gemm_tc(int epi, const __half* a_hi, const __half* a_lo, const TcWeight& w, const float* bias, const float* residual,
                  float* out_f32, __half* out_hi, __half* out_lo, int M) {
         span_begin(0);
         if (profile) { stat.gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; stat.gemm_launches++; }
+        static const bool pair_env = getenv("APRIL_B200_GEMM_CLUSTER") == nullptr || atoi(getenv("APRIL_B200_GEMM_CLUSTER")) != 1;
+        const int tiles_m = (M + tc::GEMM_BM - 1) / tc::GEMM_BM, tiles_n = (w.N + tc::GEMM_BN - 1) / tc::GEMM_BN;
+        const bool pair = pair_env && tiles_m >= 2;          // CTA pairs (cta_group::2): each CTA ingests its A rows and half of the B rows
         CUtensorMap mAh = make_map_f16(a_hi, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM), mAl = make_map_f16(a_lo, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM);
-        CUtensorMap mBh = make_map_f16(w.hi, (uint64_t)w.N, (uint64_t)w.K, tc::GEMM_BN), mBl = make_map_f16(w.lo, (uint64_t)w.N, (uint64_t)w.K, tc::GEMM_BN);
+        const uint32_t bbox = pair ? tc::GEMM_BN / 2 : tc::GEMM_BN;
+        CUtensorMap mBh = make_map_f16(w.hi, (uint64_t)w.N, (uint64_t)w.K, bbox), mBl = make_map_f16(w.lo, (uint64_t)w.N, (uint64_t)w.K, bbox);
         tc::GemmArgs g{ M, w.N, w.K, w.inv_scale, bias, residual, out_f32, out_hi, out_lo };
-        const int tiles = ((M + tc::GEMM_BM - 1) / tc::GEMM_BM) * ((w.N + tc::GEMM_BN - 1) / tc::GEMM_BN);
-        const unsigned grid = (unsigned)std::min(tiles, num_sms);
-        if (npass == 3) {
-            const size_t sm = tc::GemmCfg<3>::SMEM_BYTES;
-            if (epi == tc::GE_F32) tc::gemm_tc_kernel<3, tc::GE_F32><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
-            else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
-            else if (epi == tc::GE_F32_RESIDUAL_SPLIT) tc::gemm_tc_kernel<3, tc::GE_F32_RESIDUAL_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
-            else tc::gemm_tc_kernel<3, tc::GE_DSWISH_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+        if (pair) {
+            const int work = ((tiles_m + 1) / 2) * tiles_n;
+            const unsigned grid = 2u * (unsigned)std::min(work, num_sms / 2);
+            if (npass == 3) gemm_tc_epi<3, 2>(epi, grid, mAh, mAl, mBh, mBl, g); else gemm_tc_epi<1, 2>(epi, grid, mAh, mAl, mBh, mBl, g);
         } else {
-            const size_t sm = tc::GemmCfg<1>::SMEM_BYTES;
-            if (epi == tc::GE_F32) tc::gemm_tc_kernel<1, tc::GE_F32><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
-            else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
-            else if (epi == tc::GE_F32_RESIDUAL_SPLIT) tc::gemm_tc_kernel<1, tc::GE_F32_RESIDUAL_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
-            else tc::gemm_tc_kernel<1, tc::GE_DSWISH_SPLIT><<<grid, tc::GEMM_THREADS, sm, st>>>(mAh, mAl, mBh, mBl, g);
+            const unsigned grid = (unsigned)std::min(tiles_m * tiles_n, num_sms);
+            if (npass == 3) gemm_tc_epi<3, 1>(epi, grid, mAh, mAl, mBh, mBl, g); else gemm_tc_epi<1, 1>(epi, grid, mAh, mAl, mBh, mBl, g);
         }
         launch_check();
         span_end();
@@ -923,7 +929,7 @@ public:
         // ---- stage PCM: [tail | new samples or zeros] per session ---------------------------------
         p_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
         int16_t* hp = p_pcm.as<int16_t>();
-        for (int b = 0; b < B; b++) {
+        auto stage_one = [&](int b) {
             PassItem& it = items[(size_t)b];
             StreamFraming& fr = *it.fr;
             int16_t* dst = hp + meta[(size_t)b].pcm_off;
@@ -935,6 +941,14 @@ public:
             size_t consumed = (size_t)meta[(size_t)b].n_frames * (size_t)shift;   // next frame starts here (fbank.c:198-224)
             if (consumed > n_buf) consumed = n_buf;
             fr.tail.assign(dst + consumed, dst + n_buf);
+        };
+        const int n_stage = (pcm_total * sizeof(int16_t) >= ((size_t)8 << 20)) ? std::min(B, 8) : 1;   // big passes: the copy into pinned memory is the host's largest cost
+        if (n_stage > 1) {
+            std::vector<std::thread> th;
+            for (int k = 0; k < n_stage; k++) th.emplace_back([&, k] { for (int b = k; b < B; b += n_stage) stage_one(b); });   // sessions are disjoint
+            for (auto& t : th) t.join();
+        } else {
+            for (int b = 0; b < B; b++) stage_one(b);
         }
         cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
         CK(cudaEventRecord(ev0, st));

@@ -52,6 +52,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// one L2 read delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+// 2-CTA (cta_group::2) forms: the load may signal an mbarrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_tc(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) { asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank_tc() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_tc() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -88,6 +105,27 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // 32 lanes x 32 columns of fp32: thread i of the warp receives lane (quarter base + i)
+// D[tmem of both CTAs] (+)= A[smem, each CTA its M half] * B[smem, each CTA its N half]^T, issued by the pair's leader
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// tcgen05.commit arriving on the barrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(
@@ -143,21 +181,28 @@ struct GemmArgs {
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 256, GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int GEMM_EPI_WARPS = 8;     // two per TMEM lane quarter, alternating 32-column chunks (the DoubleSwish + split epilogue of FF1 is
+                                      // ~40 instructions per element: with 4 warps it, not the MMA, paced that GEMM)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 
-template <int NPASS> struct GemmCfg {
+template <int NPASS, int CL = 1> struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;                    // 16 KB
-    static constexpr int B_BYTES = GEMM_BN * GEMM_BK * 2;                    // 32 KB
+    static constexpr int B_BYTES = (GEMM_BN / CL) * GEMM_BK * 2;             // 32 KB; a CTA of a pair holds half of the N rows
     static constexpr int STAGE_BYTES = (NPASS == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = NPASS == 3 ? 2 : 4;
+    static constexpr int STAGES = (NPASS == 3 ? 2 : 4) + (CL == 2 ? 1 : 0);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int NPASS, int EPI>
+// CL = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x 256 tile: CTA `rank` holds rows
+// [rank * 128, +128) of A and N-rows [rank * 128, +128) of B in its own shared memory, the leader (rank 0) issues one
+// M = 256 MMA that reads both halves, and each CTA's TMEM receives its 128 rows x 256 columns. Per k-block a CTA then
+// ingests 64 KB instead of 96 KB for the same 128 x 256 outputs; the kernel is bound by what an SM can ingest
+// (~25 B/clk measured), not by the tensor pipe (12 MMAs of 128 clk per k-block).
+template <int NPASS, int EPI, int CL = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, GemmArgs g) {
-    using Cfg = GemmCfg<NPASS>;
+    using Cfg = GemmCfg<NPASS, CL>;
     constexpr int S = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -171,17 +216,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (g.N + GEMM_BN - 1) / GEMM_BN;
-    const int num_tiles = tiles_m * tiles_n;
     const int nkb = (g.K + GEMM_BK - 1) / GEMM_BK;
+    // work item w = (group of CL vertically adjacent m-tiles, n-tile); CTA `rank` of the pair takes m-tile group * CL + rank
+    // (past the last tile for odd tiles_m: its A loads are zero-filled by TMA and its epilogue stores nothing)
+    const int rank = CL == 2 ? (int)cluster_rank_tc() : 0;
+    const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+    const int num_work = ((tiles_m + CL - 1) / CL) * tiles_n;
+    auto work_m0 = [&](int w) { return ((w / tiles_n) * CL + rank) * GEMM_BM; };
+    auto work_n0 = [&](int w) { return (w % tiles_n) * GEMM_BN; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), GEMM_EPI_WARPS * CL); }   // leader: both CTAs' epilogue warps
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (CL == 2) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_tc();                        // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -194,19 +246,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             }
             __syncwarp();
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+            for (int w = cid; w < num_work; w += ncl) {
+                const int m0 = work_m0(w), n0 = work_n0(w) + rank * (GEMM_BN / CL);   // pair: my half of the B rows
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % S; const uint32_t ph = (it / S) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_wait(empty_bar(s), ph ^ 1);               // pair: the leader's commit is multicast to both CTAs
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-                        tma_load_2d(st, &mapAhi, full_bar(s), kb * GEMM_BK, m0);
-                        tma_load_2d(st + Cfg::A_BYTES, &mapBhi, full_bar(s), kb * GEMM_BK, n0);
-                        if (NPASS == 3) {
-                            tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mapAlo, full_bar(s), kb * GEMM_BK, m0);
-                            tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, full_bar(s), kb * GEMM_BK, n0);
+                        if (CL == 2) {
+                            const uint32_t fb = mapa_tc(full_bar(s), 0);                    // everything lands on the LEADER's barrier
+                            if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes
+                            tma_load_2d_pair(st, &mapAhi, fb, kb * GEMM_BK, m0);
+                            tma_load_2d_pair(st + Cfg::A_BYTES, &mapBhi, fb, kb * GEMM_BK, n0);
+                            if (NPASS == 3) {
+                                tma_load_2d_pair(st + Cfg::A_BYTES + Cfg::B_BYTES, &mapAlo, fb, kb * GEMM_BK, m0);
+                                tma_load_2d_pair(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, fb, kb * GEMM_BK, n0);
+                            }
+                        } else {
+                            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                            tma_load_2d(st, &mapAhi, full_bar(s), kb * GEMM_BK, m0);
+                            tma_load_2d(st + Cfg::A_BYTES, &mapBhi, full_bar(s), kb * GEMM_BK, n0);
+                            if (NPASS == 3) {
+                                tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &mapAlo, full_bar(s), kb * GEMM_BK, m0);
+                                tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, full_bar(s), kb * GEMM_BK, n0);
+                            }
                         }
                     }
                     __syncwarp();
@@ -214,11 +277,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: convergent warp, one elected lane issues =====================
-        {
-            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, GEMM_BN);
+        // ===================== MMA issuer (pair: the leader CTA only): convergent warp, one elected lane issues ==========
+        if (CL == 1 || rank == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM * CL, GEMM_BN);
             uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+            for (int w = cid; w < num_work; w += ncl, tcount++) {
                 const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
                 mbar_wait(tempty_bar(acc), aph ^ 1);
                 tc_fence_after();
@@ -232,22 +295,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     const uint64_t alo = make_sw128_desc(st + Cfg::A_BYTES + Cfg::B_BYTES), blo = make_sw128_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
                     const uint32_t first = kb != 0;
                     if (elect_one()) {
+                        auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) { if (CL == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum); else umma_f16(d_tmem, ad, bd, idesc, accum); };
                         if (NPASS == 3) {
 #pragma unroll
-                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, first || k != 0);
+                            for (int k = 0; k < GEMM_BK / 16; k++) mma(ahi + 2 * k, blo + 2 * k, first || k != 0);
 #pragma unroll
-                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, 1);
+                            for (int k = 0; k < GEMM_BK / 16; k++) mma(alo + 2 * k, bhi + 2 * k, 1);
 #pragma unroll
-                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
+                            for (int k = 0; k < GEMM_BK / 16; k++) mma(ahi + 2 * k, bhi + 2 * k, 1);
                         } else {
 #pragma unroll
-                            for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, first || k != 0);
+                            for (int k = 0; k < GEMM_BK / 16; k++) mma(ahi + 2 * k, bhi + 2 * k, first || k != 0);
                         }
-                        umma_commit(empty_bar(s));         // smem stage free once these MMAs have read it
+                        if (CL == 2) umma_commit_pair(empty_bar(s), 0x3); else umma_commit(empty_bar(s));   // stage free once these MMAs have read it
                     }
                     __syncwarp();
                 }
-                if (elect_one()) umma_commit(tfull_bar(acc));   // accumulator complete
+                if (elect_one()) { if (CL == 2) umma_commit_pair(tfull_bar(acc), 0x3); else umma_commit(tfull_bar(acc)); }   // accumulator complete (in both CTAs)
                 __syncwarp();
             }
         }
@@ -255,14 +319,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int q = warp & 3;                            // TMEM lane quarter this warp may access
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+        for (int w = cid; w < num_work; w += ncl, tcount++) {
             const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
-            const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+            const int m0 = work_m0(w), n0 = work_n0(w);
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
 #pragma unroll 1
-            for (int c = 0; c < GEMM_BN / 32; c++) {
+            for (int c = (warp - 2) >> 2; c < GEMM_BN / 32; c += GEMM_EPI_WARPS / 4) {
                 const int nb = n0 + c * 32;
                 if (nb >= g.N) break;                      // warp-uniform
                 float v[32];
@@ -301,12 +365,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) { if (CL == 2 && rank != 0) mbar_arrive_cluster(mapa_tc(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc)); }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (CL == 2) cluster_sync_tc();                        // no exit while the peer may still read my operands or signal my barriers
+    if (warp == 1) { if (CL == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------

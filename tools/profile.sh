@@ -1,0 +1,19 @@
+#!/bin/bash
+# Profiling pass on the GPU box (see /opt/skills/guides/B200_PROFILING.md): launch list + one `--set full` capture per hot kernel.
+# Numbers printed by bench.py under ncu are NOT bench values.
+set -u
+OUT=gpurun_out/prof; mkdir -p $OUT
+BENCH="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
+python -c "import sys; sys.path.insert(0,'tests'); sys.path.insert(0,'tools'); import common; common.model_path('full')"   # generate the model once
+
+cap() {   # name, kernel regex, launch-skip
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" --launch-skip $3 -c 1 -o $OUT/$1 -f $BENCH > $OUT/$1.log 2>&1
+  ncu -i $OUT/$1.ncu-rep --page raw --csv > $OUT/$1.raw.csv 2>/dev/null
+}
+
+cap gemm_wih "gemm_tc_kernel<3, 0, 2>" 1
+cap gemm_ff1 "gemm_tc_kernel<3, 2, 2>" 1
+
+
+
+ls -la $OUT
