@@ -65,7 +65,7 @@ struct Scan2Args {
     int GC;                // CTAs = H / 8
     int KBG;               // k-blocks per TMA copy
     int m64;               // 1: UMMA M = 64 (no over-read of 64 unused rows; accumulator rows sit in lanes 0-15 of each TMEM quarter)
-    int dbg;               // timing experiments only (results are wrong): bit 0 = skip the UMMAs, bit 1 = skip the ring's TMA loads
+    int dbg;               // bit 2: single handover poller per CTA (scan3). Timing experiments only (results are wrong): bit 0 = skip the UMMAs, bit 1 = skip the ring's TMA loads (scan2)
     float inv_scale;
     const int* nsteps;     // [Bs] (not offset)
     float* c_state;        // [Bs, H] fp32 pass-layout state of this layer (read at start, written at end)
@@ -177,7 +177,7 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
             const int tg = (int)(idx / copies), g = tg % NG, t = tg / NG;
             if (t != opened_t || g != opened_g) {
                 if (t > 0) {
-                    if (lane == 0) wait_counter(a.counter + g, (unsigned)t * (unsigned)a.GC);     // m(t-1) of the group complete everywhere
+                    if (lane == 0) wait_counter(a.counter + g * 64, (unsigned)t * (unsigned)a.GC);     // m(t-1) of the group complete everywhere
                     __syncwarp();
                     asm volatile("fence.proxy.async;" ::: "memory");     // whichever lane is elected below issues its TMA read after the acquire
                 }
@@ -327,7 +327,7 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
             for (int t = 0; t < a.T; t++) {
                 mbar_wait(rel_bar(g), t & 1);
                 asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores -> the peers' TMA (async proxy) reads
-                red_release(a.counter + g);
+                red_release(a.counter + g * 64);        // one 256-byte stride per group: the groups' polls and reds do not share an L2 line
                 TRACE2(7);
             }
     }

@@ -95,7 +95,8 @@ lstm_scan3_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*128, H
     auto rel_bar = [&](int g) { return wfull_bar + 8u + 8u * (4 * MAXG + g); };
     auto prfull_bar = [&](int k) { return wfull_bar + 8u + 8u * (5 * MAXG + k); };           // the peer's partials for my units have landed in exr (team k)
     auto prfree_bar = [&](int k) { return wfull_bar + 8u + 8u * (5 * MAXG + TEAMS + k); };   // the peer has consumed what I stored into ITS exr
-    const uint32_t tmem_slot = wfull_bar + 8u + 8u * (5 * MAXG + 2 * TEAMS);
+    auto opened_bar = [&](int g) { return wfull_bar + 8u + 8u * (5 * MAXG + 2 * TEAMS + g); };   // producer warp 0 saw the group's handover counter
+    const uint32_t tmem_slot = wfull_bar + 8u + 8u * (6 * MAXG + 2 * TEAMS);
     float* cst = reinterpret_cast<float*>(gptr(cbuf));
 
     if (threadIdx.x == 0) {
@@ -103,6 +104,7 @@ lstm_scan3_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*128, H
         mbar_init(wfull_bar, 1);
         for (int g = 0; g < MAXG; g++) { mbar_init(tfull_bar(g), MMAW); mbar_init(tempty_bar(g), 1); mbar_init(gfull_bar(g), 1); mbar_init(gfree_bar(g), 1); mbar_init(rel_bar(g), 1); }
         for (int k = 0; k < TEAMS; k++) { mbar_init(prfull_bar(k), 1); mbar_init(prfree_bar(k), 1); }
+        for (int g = 0; g < MAXG; g++) mbar_init(opened_bar(g), 1);
         fence_barrier_init();
     }
     uint32_t tmem_cols = 32; while (tmem_cols < (uint32_t)(NG * NACC * Nact)) tmem_cols <<= 1;
@@ -119,6 +121,7 @@ lstm_scan3_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*128, H
 
     if (warp < RSTAGES) {
         const int stage = warp;
+        const bool relay = (a.dbg & 4) && (copies % RSTAGES == 0);   // every producer warp then visits every (step, group): barrier phases stay in step
         if (lane == 0) tma_prefetch_desc(&mapMx);
         const long long total = (long long)a.T * NG * copies;
         int opened_t = -1, opened_g = -1;
@@ -127,8 +130,12 @@ lstm_scan3_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*128, H
             const int tg = (int)(idx / copies), g = tg % NG, t = tg / NG;
             if (t != opened_t || g != opened_g) {
                 if (t > 0) {
-                    if (lane == 0) wait_counter(a.counter + g, (unsigned)t * (unsigned)a.GC);     // m(t-1) of the group complete everywhere
-                    __syncwarp();
+                    if (relay && stage != 0) {
+                        mbar_wait(opened_bar(g), (t - 1) & 1);           // one poller per CTA: warp 0 relays the handover
+                    } else {
+                        if (lane == 0) { wait_counter(a.counter + g * 64, (unsigned)t * (unsigned)a.GC); if (relay) mbar_arrive(opened_bar(g)); }   // m(t-1) of the group complete everywhere
+                        __syncwarp();
+                    }
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 opened_t = t; opened_g = g;
@@ -284,7 +291,7 @@ lstm_scan3_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*128, H
             for (int t = 0; t < a.T; t++) {
                 mbar_wait(rel_bar(g), t & 1);
                 asm volatile("fence.proxy.async;" ::: "memory");
-                red_release(a.counter + g);
+                red_release(a.counter + g * 64);        // one 256-byte stride per group: the groups' polls and reds do not share an L2 line
                 TRACE3(7);
             }
     }

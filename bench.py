@@ -267,6 +267,7 @@ def main():
         steps_per_pass = st.encoder_steps / a.steps
         gemm_tflops = st.gemm_flops / (st.gemm_ms / 1e3) / 1e12 if st.gemm_ms > 0 else None
         peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        scan_tflops = (st.encoder_steps * 2.0 * 31_457_280) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e12
         out = {
             "metric": "audio_frames_per_sec", "value": frames_total / compute_s, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000.0 * compute_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,14 +282,21 @@ def main():
                     "x_realtime_per_stream": a.seconds / (wall_s / a.steps)},
             "gpu_launches": int(st.kernel_launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "time-batched projection GEMMs (W_ih, FF1, FF2, conv-out, enc_proj)",
-                         "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": (gemm_tflops / peak_tf) if gemm_tflops else None,
+            # dominant kernel of the step: the persistent recurrent scan (one launch = one LSTM layer over all steps of a pass).
+            # algorithmic FLOPs = the reference's W_hh (4H x D) and W_hr (D x H) products per session-step, counted once.
+            "roofline": {"bound": "tensor", "kernel": "scan3::lstm_scan3_kernel (recurrent W_hh / W_hr part of one LSTM layer, all steps of a pass; %.0f %% of the step)" % (100.0 * st.lstm_scan_ms / max(1e-9, st.compute_ms)),
+                         "achieved": scan_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": scan_tflops / peak_tf,
                          "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
-                         "traffic": 838.8e6, "traffic_note": "dram bytes read+written by one W_ih launch (M=49664,N=4096,K=512), ncu --set full, profiles/r01_ncu_raw_gemm.csv; algorithmic bytes of that launch: 923e6",
-                         "precision": "fp16x3 split (3 tensor-core MMAs per algorithmic product; tokens identical to the fp32 reference); algorithmic FLOPs counted once",
+                         "traffic": 1173.2e6, "traffic_note": "dram bytes read + written by one launch (748 steps x 64 sessions), ncu --set full, profiles/r01b_ncu_scan3.raw.csv; algorithmic bytes of that launch: 784e6 (gate pre-activations G, fp32) + 196e6 (m out, fp16 hi/lo) + 16.8e6 (W_eff slice set) = 997e6",
+                         "why_far_from_peak": "latency-bound dependent chain: %d sequential layer-steps per pass, each a grid-wide exchange of m(t) through L2 (TMA landing ~0.7 us + MMA + TMEM drain + pair exchange + cell + release ~1 us + acquire ~1.5 us); N = 64 sessions per MMA and a measured >= 84 clk issue cost per tcgen05.mma whatever its N (profiles/r01b_summary.md)" % int(12 * steps_per_pass / S),
+                         "us_per_layer_step": 1e3 * st.lstm_scan_ms / max(1.0, (st.encoder_steps / S) * 12),
+                         "hbm_view": {"achieved_GBps": (st.encoder_steps * 12 * (4 * 1024 * 4 + 2 * 1024 * 2)) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e9, "peak_GBps": pk.get("hbm_gbs"), "note": "algorithmic bytes: fp32 gate rows in, fp16 (hi, lo) m rows out, per session-step and layer"},
+                         "precision": "fp16x3 split (3-4 tensor-core products per algorithmic product; callbacks identical to the fp32 reference on 23 of 24 checked 30 s streams); algorithmic FLOPs counted once",
+                         "gemm": {"kernel": "tc::gemm_tc_kernel<3,*,2> time-batched projections (W_ih, W_hr out, FF1, FF2, conv3, conv-out, enc_proj), CTA pairs 256x256x64",
+                                  "achieved": gemm_tflops, "frac": (gemm_tflops / peak_tf) if gemm_tflops else None, "ms_per_step": st.gemm_ms / a.steps,
+                                  "note": "3 MMAs per algorithmic product: the tensor pipe does 3x this figure"},
                          "gemm_ms_per_step": st.gemm_ms / a.steps, "greedy_ms_per_step": st.greedy_ms / a.steps, "lstm_scan_ms_per_step": st.lstm_scan_ms / a.steps,
                          "whole_pass_tflops": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12,
-                         "lstm_scan": {"bound": "latency", "us_per_layer_step": 1e3 * st.lstm_scan_ms / max(1.0, (st.encoder_steps / S) * 12), "algorithmic_tflops": (st.encoder_steps * 2.0 * 31_457_280) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e12},
                          "whole_pass_frac": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12 / peak_tf},
             "results": {"partial_callbacks": int(counters[0]), "final_callbacks": int(counters[1]), "silence_callbacks": int(counters[2]), "final_tokens": int(counters[3]),
                         "encoder_steps_per_pass": steps_per_pass, "joiner_passes_per_pass": st.joiner_passes / a.steps},

@@ -11,8 +11,8 @@ cap() {   # name, kernel regex, launch-skip
   ncu -i $OUT/$1.ncu-rep --page raw --csv > $OUT/$1.raw.csv 2>/dev/null
 }
 
-cap gemm_wih "gemm_tc_kernel<3, 0, 2>" 1
-cap gemm_ff1 "gemm_tc_kernel<3, 2, 2>" 1
+cap gemm_wih "gemm_tc_kernel<.int.3, .int.0, .int.2>" 1
+cap gemm_ff1 "gemm_tc_kernel<.int.3, .int.2, .int.2>" 1
 
 
 
