@@ -173,6 +173,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL_DEBUG=VERSION/INFO prints to stdout, which must carry exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     os.environ["APRIL_B200_DEVICE"] = str(local)

@@ -5,15 +5,14 @@ set -u
 OUT=gpurun_out/prof; mkdir -p $OUT
 BENCH="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
 python -c "import sys; sys.path.insert(0,'tests'); sys.path.insert(0,'tools'); import common; common.model_path('full')"   # generate the model once
-
-cap() {   # name, kernel regex, launch-skip
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file $OUT/launches.csv $BENCH > $OUT/launches.log 2>&1
+cap() {   # name, kernel regex (demangled name), launch-skip
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" --launch-skip $3 -c 1 -o $OUT/$1 -f $BENCH > $OUT/$1.log 2>&1
   ncu -i $OUT/$1.ncu-rep --page raw --csv > $OUT/$1.raw.csv 2>/dev/null
 }
-
+cap scan3 lstm_scan3_kernel 0
 cap gemm_wih "gemm_tc_kernel<.int.3, .int.0, .int.2>" 1
 cap gemm_ff1 "gemm_tc_kernel<.int.3, .int.2, .int.2>" 1
-
-
-
-ls -la $OUT
+cap greedy greedy_cluster_kernel 0
+cap fbank fbank_kernel 0
+ls -la $OUT | grep -v ncu-rep
