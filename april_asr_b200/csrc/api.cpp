@@ -153,7 +153,7 @@ APRIL_EXPORT int aab_set_device(int device) {
     return 0;
 }
 
-APRIL_EXPORT const char* aab_engine_version(void) { return "april-b200 r1 (sm_100a; exact fp32 tier + tcgen05 tier)"; }
+APRIL_EXPORT const char* aab_engine_version(void) { return "april-b200 r1b (sm_100a; exact fp32 tier + tcgen05 tier: pair GEMMs, single-exchange K-split scan)"; }
 
 static int pick_device() {
     if (tl_device >= 0) return tl_device;
