@@ -143,3 +143,16 @@ def pcm_digest(pcm):
 def load_golden(name):
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)
+
+
+def callback_diff(got, want):
+    """(number of callbacks that differ after aligning the two logs, finals identical?). Finals (result type 2) are the
+    emitted text; partials can also carry one *tentative* token (april_session.c:417-422: pushed, reported, popped) that is
+    the arg-max over non-blank logits at a blank step, so a near-tie there changes one partial and nothing afterwards."""
+    import difflib
+    g = [repr(k) for k in got.keys()]
+    w = [repr(k) for k in want.keys()]
+    sm = difflib.SequenceMatcher(a=g, b=w, autojunk=False)
+    differing = sum(max(i2 - i1, j2 - j1) for tag, i1, i2, j1, j2 in sm.get_opcodes() if tag != "equal")
+    fin = lambda c: [k for k in c.keys() if k[0] == 2]
+    return differing, fin(got) == fin(want)

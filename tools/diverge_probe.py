@@ -10,16 +10,20 @@ import common as C  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--stream", type=int, default=3)
 ap.add_argument("--seconds", type=float, default=30.0)
+ap.add_argument("--model", default="full")
+ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--samples", type=int, default=0)
 ap.add_argument("--batch", type=int, default=1, help="run the stream as member of a batch of this many sessions (stream ids 0..batch-1)")
 a = ap.parse_args()
-path = C.model_path("full")
-pcm = C.gen_stream(a.stream, int(16000 * a.seconds))
+path = C.model_path(a.model)
+nsamp = a.samples or int(16000 * a.seconds)
+pcm = C.gen_stream(a.stream, nsamp)
 if a.batch > 1:
-    pcms = [C.gen_stream(i, int(16000 * a.seconds)) for i in range(a.batch)]
-    g = C.run_product_batch(path, pcms, tap=True)[a.stream]
+    pcms = [C.gen_stream(i, nsamp) for i in range(a.batch)]
+    g = C.run_product_batch(path, pcms, tap=True, chunk=a.chunk or None)[a.stream]
 else:
-    g = C.run_product_batch(path, [pcm], tap=True)[0]
-w = C.run_oracle(path, pcm, tap=True)
+    g = C.run_product_batch(path, [pcm], tap=True, chunk=a.chunk or None)[0]
+w = C.run_oracle(path, pcm, tap=True, chunk=a.chunk or None)
 n = min(len(g.enc), len(w.enc))
 err = np.array([np.abs(g.enc[t] - w.enc[t]).max() for t in range(n)])
 mag = np.array([np.abs(w.enc[t]).max() for t in range(n)])
@@ -41,3 +45,10 @@ if first is not None and first > 0:
         lw = w.logits[i]; lg = g.logits[i]
         o = np.argsort(lw)[::-1]
         print("pass", i, "oracle top3", [(int(k), float(lw[k])) for k in o[:3]], "gpu same idx", [float(lg[k]) for k in o[:3]], "blank(0)", float(lw[0]), float(lg[0]), "err", float(np.abs(lg - lw).max()))
+gk, wk = g.keys(), w.keys()
+k = next((j for j, (x, y) in enumerate(zip(gk, wk)) if x != y), None)
+print("callbacks", len(gk), len(wk), "first differing callback:", k)
+if k is not None:
+    for j in range(max(0, k - 1), min(len(gk), len(wk), k + 2)):
+        print(" gpu   ", j, gk[j][0], len(gk[j][1]), gk[j][1][:3], "...", gk[j][1][-4:])
+        print(" oracle", j, wk[j][0], len(wk[j][1]), wk[j][1][:3], "...", wk[j][1][-4:])

@@ -36,10 +36,11 @@ def main():
         g, w = got[i].keys(), want[i].keys()
         k = next((j for j, (x, y) in enumerate(zip(g, w)) if x != y), None)
         if k is None and len(g) != len(w): k = min(len(g), len(w))
-        rows.append({"session": i, "callbacks_gpu": len(g), "callbacks_oracle": len(w), "identical": k is None, "first_diff_callback": k,
+        nd, fin_ok = C.callback_diff(got[i], want[i])
+        rows.append({"session": i, "callbacks_gpu": len(g), "callbacks_oracle": len(w), "identical": k is None, "first_diff_callback": k, "callbacks_differing": nd, "finals_identical": fin_ok,
                      "final_tokens": sum(len(t) for r, t in w if r == 2)})
     print(json.dumps({"check": "full-length parity", "sessions": a.sessions, "seconds": a.seconds, "checked": a.check,
-                      "identical": sum(r["identical"] for r in rows), "gpu_wall_s": round(t_gpu, 2), "oracle_wall_s": round(t_cpu, 2), "rows": rows}))
+                      "identical": sum(r["identical"] for r in rows), "finals_identical": sum(r["finals_identical"] for r in rows), "gpu_wall_s": round(t_gpu, 2), "oracle_wall_s": round(t_cpu, 2), "rows": rows}))
 
 
 if __name__ == "__main__":
