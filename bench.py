@@ -44,7 +44,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -305,7 +305,7 @@ def main():
         if not a.no_cpu_baseline and world == 1:
             nthr = max(1, min(ncores, 32))
             fps, wall, frames = time_cpu_reference(path, a.cpu_seconds, nthr, first_id=5000)
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": nthr, "kind": "reference",
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": nthr, "kind": "reference", "per_session_frames_per_sec": fps / nthr, "per_session_x_realtime": fps / nthr / 100.0,
                                    "sample": "%d sessions x %.1f s of the same synthetic PCM, one thread per session (reference uses 1 ORT thread per session), feed + flush; %.1f s wall" % (nthr, a.cpu_seconds, wall),
                                    "note": "reference host sources compiled unmodified + CPU fp32 restatement of the ONNX graphs (ONNXRuntime unavailable in this image)"}
         print(json.dumps(out))
