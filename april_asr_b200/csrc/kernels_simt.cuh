@@ -154,6 +154,109 @@ fbank_kernel(FbankParams P, const int16_t* __restrict__ pcm, const long long* __
     }
 }
 
+// Variant (opt-in with APRIL_B200_FBANK=v2 until validated on hardware; same arithmetic, same order): the DC sum is a
+// 512-step serial chain (float accumulator over double data, fbank.c:241-246) that fbank_kernel runs on ONE lane per frame
+// (ncu: 6150 warp instructions per frame, issue-active 26 %). Here a warp owns 8 consecutive rows: lanes 0-7 run the
+// eight serial chains side by side (reading the PCM through L1), then the warp processes its rows one after the other.
+// grid (ceil(max_new_rows / 32), B), block 128.
+constexpr int FB2_RPW = 8;
+__global__ void __launch_bounds__(128)
+fbank_kernel_v2(FbankParams P, const int16_t* __restrict__ pcm, const long long* __restrict__ pcm_off,
+                const int* __restrict__ pad_before, const int* __restrict__ n_frames, const int* __restrict__ n_new,
+                const int* __restrict__ carry, float* __restrict__ FB, int row_pitch) {
+    extern __shared__ double smem_d[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int r_first = (blockIdx.x * 4 + warp) * FB2_RPW;
+    const int nn = n_new[b], pb = pad_before[b], nf = n_frames[b];
+    if (r_first >= nn) return;
+    const int N = P.N;
+    double* dat = smem_d + (size_t)warp * 3 * N;
+    double* re = dat + N;
+    double* im = re + N;
+    const int16_t* xb = pcm + pcm_off[b];
+
+    // the eight DC means of this warp's rows, one serial chain per lane
+    float mean_l = 0.f;
+    if (lane < FB2_RPW) {
+        const int r = r_first + lane;
+        if (r < nn && r >= pb && r < pb + nf) {
+            const int16_t* x = xb + (long long)(r - pb) * P.shift;
+            float sum = 0.f;
+            for (int j = 0; j < N; j++) sum = (float)((double)sum + (double)((float)x[j] / 32768.0f));
+            mean_l = sum / (float)N;
+        }
+    }
+    for (int k = 0; k < FB2_RPW; k++) {
+        const int r = r_first + k;
+        if (r >= nn) break;                                              // warp-uniform
+        float* out = FB + ((size_t)b * row_pitch + carry[b] + r) * P.mel;
+        const float mean = __shfl_sync(0xffffffffu, mean_l, k);
+        if (!(r >= pb && r < pb + nf)) {                                 // fbank_flush pad rows, fbank.c:312-316
+            for (int m = lane; m < P.mel; m += 32) out[m] = P.pad_value;
+            continue;
+        }
+        const int16_t* x = xb + (long long)(r - pb) * P.shift;
+        for (int j = lane; j < N; j += 32) dat[j] = (double)((float)x[j] / 32768.0f);
+        __syncwarp();
+        const double dmean = (double)mean;
+        const double coeff = (double)0.97f;
+        for (int base = 0; base < N; base += 32 * 8) {
+            double cur[8], prev[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int j = base + u * 32 + lane;
+                cur[u] = __dsub_rn(dat[j], dmean);
+                prev[u] = __dsub_rn(dat[j > 0 ? j - 1 : 0], dmean);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int j = base + u * 32 + lane;
+                double v = __dsub_rn(cur[u], __dmul_rn(coeff, prev[u]));
+                v = __dmul_rn(v, (double)P.window[j]);
+                int rj = __brev((unsigned)j) >> (32 - P.log2N);
+                re[rj] = v;
+                im[rj] = 0.0;
+            }
+            __syncwarp();
+        }
+        for (int s = 1; s <= P.log2N; s++) {
+            const int half = 1 << (s - 1);
+            const int tw_stride = N >> s;
+            for (int j = lane; j < N / 2; j += 32) {
+                int pos = j & (half - 1);
+                int i0 = ((j >> (s - 1)) << s) + pos;
+                int i1 = i0 + half;
+                double2 w = P.twiddle[pos * tw_stride];
+                double xr = re[i1], xi = im[i1];
+                double tr = w.x * xr - w.y * xi;
+                double ti = w.x * xi + w.y * xr;
+                double ar = re[i0], ai = im[i0];
+                re[i0] = ar + tr; im[i0] = ai + ti;
+                re[i1] = ar - tr; im[i1] = ai - ti;
+            }
+            __syncwarp();
+        }
+        float* pw = (float*)dat;
+        for (int kbin = lane; kbin < P.nbins; kbin += 32) {
+            float fr = (float)re[kbin];
+            float fi = kbin == 0 ? 0.f : (float)im[kbin];
+            pw[kbin] = __fadd_rn(__fmul_rn(fr, fr), __fmul_rn(fi, fi));
+        }
+        __syncwarp();
+        for (int m = lane; m < P.mel; m += 32) {
+            const int k0 = P.mel_start[m], cnt = P.mel_count[m];
+            const float* w = P.mel_w + P.mel_off[m];
+            float val = 0.f;
+            for (int i = 0; i < cnt; i++) val = __fadd_rn(val, __fmul_rn(pw[k0 + i], w[i]));
+            const float kEps = 1.1920928955078125e-07f;
+            out[m] = (float)log((double)fmaxf(kEps, val));
+        }
+        __syncwarp();                                                    // dat / re / im are reused by the next row
+    }
+}
+
 // copy carried-over feature rows (<= carry_cap per session) into the pass buffer and back
 __global__ void carry_in_kernel(const float* __restrict__ carry_store, const int* __restrict__ slot, const int* __restrict__ carry,
                                 float* __restrict__ FB, int row_pitch, int mel, int carry_cap) {

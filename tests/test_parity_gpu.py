@@ -235,3 +235,25 @@ def test_long_form_carry_over_in_many_small_feeds():
         assert finals_ok, "session %d: final results differ" % i
         assert nd <= 3, "session %d: %d callbacks differ" % (i, nd)      # tentative-token near-ties only (see common.callback_diff)
         assert len(want[i].log) > 500
+
+
+@pytest.mark.xfail(strict=False, reason="fbank_kernel_v2 was written after this round's GPU budget was spent: opt-in (APRIL_B200_FBANK=v2), not yet run on hardware")
+def test_fbank_v2_variant_is_bit_compatible():
+    """Same golden rows through the opt-in front-end variant (eight DC-sum chains per warp). Runs in a subprocess because the
+    switch is read once per process."""
+    import subprocess, sys
+    code = (
+        "import os, sys, ctypes, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import april_asr_b200 as A, common as C\n"
+        "g = np.load(os.path.join(C.GOLDEN, 'fbank_stream0_3s.npz')); pcm = C.gen_stream(0, 48000)\n"
+        "lib = C.product_lib(); m = A.Model(C.TINY_MODEL, lib); out = np.zeros((400, 80), np.float32)\n"
+        "n = lib.c.aab_debug_fbank(m.handle, pcm.ctypes.data_as(ctypes.POINTER(ctypes.c_short)), pcm.size, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 400)\n"
+        "ref = g['rows']; assert n == ref.shape[0]\n"
+        "mism = int((out[:n].view(np.uint32) != ref.view(np.uint32)).sum()); print('mismatching', mism)\n"
+        "assert np.abs(out[:n] - ref).max() <= 2e-6 and mism <= ref.size // 1000\n"
+        "cols = C.run_product_batch(C.TINY_MODEL, [C.gen_stream(2, 64000)]); want = C.load_golden('tiny_callbacks.json')['stream2']\n"
+    ) % (C.ROOT, os.path.join(C.ROOT, "tests"), os.path.join(C.ROOT, "tools"))
+    env = dict(os.environ, APRIL_B200_FBANK="v2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
