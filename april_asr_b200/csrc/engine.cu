@@ -697,9 +697,8 @@ public:
             const int KBW = scan3 ? KBH / 2 : KBH;                                                 // k-blocks a CTA walks per step
             a.KBG = 1; for (int kk = 1; kk <= KBW; kk++) if (KBW % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
             static const bool m64_env = !(getenv("APRIL_B200_SCAN_M128"));
-            static const int dbg_env = getenv("APRIL_B200_SCAN_DBG") ? atoi(getenv("APRIL_B200_SCAN_DBG")) : 0;
             static const bool norelay_env = getenv("APRIL_B200_SCAN_NORELAY") != nullptr;
-            a.dbg = dbg_env | (norelay_env ? 0 : 4);     // bit 2: one handover poller per CTA, relayed to the other producer warps (-2.3 % measured)
+            a.dbg = norelay_env ? 0 : 4;     // bit 2: one handover poller per CTA, relayed to the other producer warps (-2.3 % measured)
             a.m64 = m64_env ? 1 : 0;
             a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.c_state = cw; a.m_state = mw;
             a.Mx = Mx; a.Mall_hi = b_mall_h.as<__half>(); a.Mall_lo = b_mall_l.as<__half>(); a.counter = scan_counters;

@@ -65,7 +65,7 @@ struct Scan2Args {
     int GC;                // CTAs = H / 8
     int KBG;               // k-blocks per TMA copy
     int m64;               // 1: UMMA M = 64 (no over-read of 64 unused rows; accumulator rows sit in lanes 0-15 of each TMEM quarter)
-    int dbg;               // bit 2: single handover poller per CTA (scan3). Timing experiments only (results are wrong): bit 0 = skip the UMMAs, bit 1 = skip the ring's TMA loads (scan2)
+    int dbg;               // option bits: 4 = single handover poller per CTA (scan3)
     float inv_scale;
     const int* nsteps;     // [Bs] (not offset)
     float* c_state;        // [Bs, H] fp32 pass-layout state of this layer (read at start, written at end)
@@ -187,12 +187,9 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
             const uint32_t use = (uint32_t)(idx / RSTAGES);
             mbar_wait(empty_bar(stage), (use & 1) ^ 1);                  // stage free (in every CTA of the cluster)
             if (elect_one()) {
-                if (a.dbg & 2) mbar_arrive(full_bar(stage));
-                else {
-                    mbar_expect_tx(full_bar(stage), SB);
-                    if (CS == 1) tma_load_5d(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t);   // row t holds m(t-1)
-                    else if ((uint32_t)j % CS == crank) tma_load_5d_mc(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t, cmask);
-                }
+                mbar_expect_tx(full_bar(stage), SB);
+                if (CS == 1) tma_load_5d(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t);   // row t holds m(t-1)
+                else if ((uint32_t)j % CS == crank) tma_load_5d_mc(ring0 + stage * SB, &mapMx, full_bar(stage), 0, a.g0 + a.goff[g], 0, j * a.KBG, t, cmask);
             }
             __syncwarp();
             if (j == copies - 1 && lane == 0) TRACE2(1);
@@ -227,11 +224,10 @@ lstm_scan2_kernel(const __grid_constant__ CUtensorMap mapW,    // 2-D [GC*64, H]
                     if (j == 0 && mw == 0 && lane == 0) TRACE2(2);
                     tc_fence_after();
                     if (elect_one()) {
-                        if (!(a.dbg & 1))
-                            for (int kk = 0; kk < a.KBG; kk++) {
-                                const uint64_t ad = make_sw128_desc(base + (j * a.KBG + kk) * w_kb_bytes), bd = make_sw128_desc(ring0 + s * SB + kk * KBB);
-                                umma_f16(d_tmem, ad + 2 * mw, bd + 2 * mw, idesc, (j | kk) != 0);
-                            }
+                        for (int kk = 0; kk < a.KBG; kk++) {
+                            const uint64_t ad = make_sw128_desc(base + (j * a.KBG + kk) * w_kb_bytes), bd = make_sw128_desc(ring0 + s * SB + kk * KBB);
+                            umma_f16(d_tmem, ad + 2 * mw, bd + 2 * mw, idesc, (j | kk) != 0);
+                        }
                         if (CS == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
                     }
                     __syncwarp();
