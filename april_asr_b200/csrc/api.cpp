@@ -353,4 +353,28 @@ APRIL_EXPORT int aab_debug_gemm(AprilASRModel model, int tier, int M, int N, int
     return model->engine->debug_gemm(tier, M, N, K, A, W, bias, out);
 }
 
+APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_records, const int* max_idx, const float* max_val, const float* blank_val,
+                                  int flush, AprilRecognitionResultHandler handler, void* userdata) {
+    if (!model_path || !handler || n_steps < 0 || n_records < 0 || (n_records && (!max_idx || !max_val || !blank_val))) return -1;
+    LoadedModel lm;
+    std::string err;
+    if (!load_april_file(model_path, lm, err)) { LOG_ERROR("aab_debug_replay: failed to read model: %s", err.c_str()); return -1; }
+    Vocab vocab;
+    vocab.tokens = lm.params.tokens; vocab.blank_id = lm.params.blank_id;
+    TokenShaper shaper(&vocab, handler, userdata);
+    const size_t stride = (size_t)lm.params.segment_step * (size_t)lm.params.frame_shift_ms;   // fbank.c:359-361
+    int r = 0;
+    for (int t = 0; t < n_steps; t++) {
+        shaper.begin_step(stride);
+        for (int p = 0; p < 3; p++) {                                  // april_session.c:449-454
+            if (r >= n_records) return -1;
+            const bool blank = shaper.on_joiner_pass(p == 0 ? 1.0f : 0.0f, max_idx[r], max_val[r], blank_val[r]);
+            r++;
+            if (blank) break;
+        }
+    }
+    if (flush) shaper.on_flush_end();
+    return r;
+}
+
 }  // extern "C"

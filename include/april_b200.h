@@ -80,6 +80,15 @@ APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t
  * (tier 0 = fp32 SIMT, 1 = fp16 tcgen05, 3 = fp16x3 split tcgen05). Host pointers. */
 APRIL_EXPORT int aab_debug_gemm(AprilASRModel model, int tier, int M, int N, int K, const float* A, const float* W, const float* bias, float* out);
 
+/* Test hook, CPU only (no device needed): the host half of the greedy search and the result shaping
+ * (april_session.c:199-429 as re-implemented in session.cpp) driven by a recorded stream of joiner-pass summaries.
+ * Reads only the vocabulary / parameters of `model_path`. For each of n_steps encoder steps it consumes up to three
+ * records (max_idx = arg-max over non-blank ids, max_val, blank_val) exactly as aas_infer does (early_emit 1, 0, 0; stop at
+ * the first blank), calling `handler` like a session would; `flush` != 0 appends the tail of aas_flush. Returns the number
+ * of records consumed, or -1. */
+APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_records, const int* max_idx, const float* max_val, const float* blank_val,
+                                  int flush, AprilRecognitionResultHandler handler, void* userdata);
+
 APRIL_EXPORT const char* aab_engine_version(void);
 
 #ifdef __cplusplus
