@@ -17,6 +17,7 @@
 #include "engine.h"
 #include "model_loader.h"
 #include "session.h"
+#include "plan.h"
 
 using namespace april;
 
@@ -375,6 +376,23 @@ APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_rec
     }
     if (flush) shaper.on_flush_end();
     return r;
+}
+
+APRIL_EXPORT int aab_debug_plan(const char* model_path, int n_calls, const size_t* counts, const int* flush, int* out_steps, int* out_frames) {
+    if (!model_path || n_calls < 0 || (n_calls && (!counts || !flush || !out_steps || !out_frames))) return -1;
+    LoadedModel lm;
+    std::string err;
+    if (!load_april_file(model_path, lm, err)) { LOG_ERROR("aab_debug_plan: failed to read model: %s", err.c_str()); return -1; }
+    const Params& prm = lm.params;
+    int N = prm.frame_length_ms * prm.sample_rate / 1000;              // engine.cu: same derivation (fbank.c:136-141)
+    const int shift = prm.frame_shift_ms * prm.sample_rate / 1000;
+    if (prm.round_pow2) { int p2 = 1; while (p2 < N) p2 <<= 1; N = p2; }
+    PlanState st;
+    for (int i = 0; i < n_calls; i++) {
+        const PassPlan pl = plan_pass(st, counts[i], flush[i] != 0, prm.segment_size, prm.segment_step, N, shift, 6400);   // april_session.c:500,555-556
+        out_steps[i] = pl.nsteps; out_frames[i] = pl.n_frames;
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // Engine implementation: device memory layout, pass planning (the integer logic of fbank.c's ring:
 // fbank.c:174-226,308-349) and kernel orchestration. See engine.h and DESIGN.md.
 #include "engine.h"
+#include "plan.h"
 
 #include <algorithm>
 #include <chrono>
@@ -901,30 +902,21 @@ public:
             PassMeta& m = meta[(size_t)b];
             m = PassMeta{};
             m.slot = fr.slot;
-            m.carry = (int)fr.avail;
-            long long avail = fr.avail, avail_f = fr.avail_f;
-            int steps = 0, pad_before = 0, pad_after = 0;
-            auto drain = [&]() { while (avail >= SEG) { steps++; avail -= STEP; avail_f -= STEP; } };
-            auto flush_loop = [&](int& pads) {                                   // while(fbank_flush) aas_infer
-                while (avail_f >= -(long long)(SEG * 3)) { while (avail < SEG) { pads++; avail++; } drain(); }
-            };
-            size_t n_in = it.flush ? (size_t)FLUSH_ZEROS : it.count;
-            if (it.flush) flush_loop(pad_before);
-            size_t n_buf = fr.tail.size() + n_in;
-            int nf = n_buf >= (size_t)N ? (int)((n_buf - (size_t)N) / (size_t)shift) + 1 : 0;
-            avail += nf;
-            if (nf > 0) avail_f = avail;                                          // fbank.c:299-300
-            if (it.flush) flush_loop(pad_after); else drain();
-            m.pad_before = pad_before; m.n_frames = nf; m.n_new = pad_before + nf + pad_after;
+            PlanState ps; ps.avail = fr.avail; ps.avail_f = fr.avail_f; ps.tail = fr.tail.size();
+            const PassPlan pl = plan_pass(ps, it.count, it.flush, SEG, STEP, N, shift, (size_t)FLUSH_ZEROS);   // plan.h: CPU-tested against the oracle
+            const int steps = pl.nsteps, nf = pl.n_frames;
+            const size_t n_buf = pl.n_buf;
+            m.carry = pl.carry;
+            m.pad_before = pl.pad_before; m.n_frames = nf; m.n_new = pl.n_new;
             m.nsteps = steps; m.flush_flag = it.flush ? 1 : 0;
-            m.keep_first = steps * STEP; m.n_keep = m.carry + m.n_new - steps * STEP;
-            if (m.n_keep != (int)avail || m.n_keep > CARRY_CAP || m.n_keep < 0) { fprintf(stderr, "libapril: (engine) [ERROR] internal: carry accounting\n"); abort(); }
+            m.keep_first = pl.keep_first; m.n_keep = pl.n_keep;
+            if (m.n_keep != (int)ps.avail || m.n_keep > CARRY_CAP || m.n_keep < 0) { fprintf(stderr, "libapril: (engine) [ERROR] internal: carry accounting\n"); abort(); }
             m.pcm_off = (long long)pcm_total;
             pcm_total += (n_buf + 7) & ~(size_t)7;
             max_new = std::max(max_new, m.n_new);
             max_rows = std::max(max_rows, m.carry + m.n_new);
             Tmax = std::max(Tmax, steps);
-            fr.avail = avail; fr.avail_f = avail_f; fr.steps_total += steps;
+            fr.avail = ps.avail; fr.avail_f = ps.avail_f; fr.steps_total += steps;
             it.n_steps = steps;
             stat.frames += (uint64_t)nf;
             stat.encoder_steps += (uint64_t)steps;

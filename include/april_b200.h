@@ -89,6 +89,11 @@ APRIL_EXPORT int aab_debug_gemm(AprilASRModel model, int tier, int M, int N, int
 APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_records, const int* max_idx, const float* max_val, const float* blank_val,
                                   int flush, AprilRecognitionResultHandler handler, void* userdata);
 
+/* Test hook, CPU only: the pass planner (plan.h: frame counts, flush padding, encoder steps per call) for one stream fed
+ * with n_calls calls; call i feeds counts[i] samples, or is an aas_flush when flush[i] != 0. Writes the encoder steps and
+ * the frames computed per call. Returns 0, or -1 on a bad model file. */
+APRIL_EXPORT int aab_debug_plan(const char* model_path, int n_calls, const size_t* counts, const int* flush, int* out_steps, int* out_frames);
+
 APRIL_EXPORT const char* aab_engine_version(void);
 
 #ifdef __cplusplus
