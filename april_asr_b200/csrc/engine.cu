@@ -764,7 +764,7 @@ public:
         }
     }
 
-    static bool fbank_v2() { static const bool v = getenv("APRIL_B200_FBANK") && !strcmp(getenv("APRIL_B200_FBANK"), "v2"); return v; }   // opt-in until validated on hardware
+    static bool fbank_v2() { static const bool v = getenv("APRIL_B200_FBANK") && !strcmp(getenv("APRIL_B200_FBANK"), "v2"); return v; }   // opt-in until its speed is measured
 
     template <int NP, int EPI, int CL> void gemm_tc_launch(unsigned grid, const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, const tc::GemmArgs& g) {
         bool& attr_done = gemm_attr[(NP == 3 ? 8 : 0) + EPI * 2 + (CL - 1)];   // per engine (= per device) and instantiation

@@ -154,7 +154,7 @@ fbank_kernel(FbankParams P, const int16_t* __restrict__ pcm, const long long* __
     }
 }
 
-// Variant (opt-in with APRIL_B200_FBANK=v2 until validated on hardware; same arithmetic, same order): the DC sum is a
+// Variant (opt-in with APRIL_B200_FBANK=v2: bit-compatible on hardware, speed not yet measured; same arithmetic, same order): the DC sum is a
 // 512-step serial chain (float accumulator over double data, fbank.c:241-246) that fbank_kernel runs on ONE lane per frame
 // (ncu: 6150 warp instructions per frame, issue-active 26 %). Here a warp owns 8 consecutive rows: lanes 0-7 run the
 // eight serial chains side by side (reading the PCM through L1), then the warp processes its rows one after the other.
