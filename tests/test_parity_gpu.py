@@ -256,3 +256,21 @@ def test_fbank_v2_variant_is_bit_compatible():
     env = dict(os.environ, APRIL_B200_FBANK="v2")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, timeout=300)
     assert r.returncode == 0, r.stderr[-500:]
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; not yet run on hardware")
+def test_async_ring_overflow_reports_cant_keep_up():
+    """audio_provider.c:59-64 / april_session.c:482-492: an async session whose 48 000-sample ring would overflow drops the
+    chunk and calls the handler with ERROR_CANT_KEEP_UP (count 0) from the feeding thread."""
+    import time
+    lib = C.product_lib()
+    m = A.Model(C.TINY_MODEL, lib)
+    col = C.Collected()
+    s = A.Session(m, col.cb, asynchronous=True, no_rt=True)
+    s.feed_pcm16(C.gen_stream(50, 100000))                # > 48 000 in one call: cannot fit whatever the batcher has drained
+    assert (3, []) in col.keys()
+    s.feed_pcm16(C.gen_stream(51, 16000))                 # a chunk that fits is still accepted afterwards
+    time.sleep(0.3)
+    s.flush(); time.sleep(0.5)
+    assert any(r in (1, 2) for r, _ in col.keys()) or len(col.keys()) >= 1
+    s.close(); m.close()
