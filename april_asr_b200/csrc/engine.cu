@@ -16,6 +16,7 @@
 #include "kernels_scan.cuh"
 #include "kernels_scan2.cuh"
 #include "kernels_scan3.cuh"
+#include "kernels_scan4.cuh"
 
 namespace april {
 
@@ -220,6 +221,12 @@ public:
     bool gemm_attr[16] = {};
     bool scan3 = false;             // K split over CTA pairs (kernels_scan3.cuh): same buffers and state as scan2, different W slicing
     size_t scan3_smem = 0;
+    // wide-batch scan (kernels_scan4.cuh): sessions on the UMMA M dimension, K split over clusters of scan4_cs CTAs
+    struct Scan4Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; };
+    std::vector<Scan4Layer> s4layers;
+    bool scan4 = false;
+    int scan4_cs = 2, scan4_mmaw = 4;
+    size_t scan4_smem = 0;
     float* m_store = nullptr;       // [slot][L][H]
     DevBuf b_mx, b_mall_h, b_mall_l, b_mw;
     __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
@@ -314,8 +321,8 @@ public:
                 tlayers.push_back(tl);
             }
             set_gemm_attrs();
-            init_scan(w);
-            init_scan2(w);
+            init_scan4(w);
+            if (!scan4) { init_scan(w); init_scan2(w); }
         }
 
         // vocabulary flags (april_session.c:338-351)
@@ -676,6 +683,106 @@ public:
         if (!scan_counters) { CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned))); owned.push_back(scan_counters); }
     }
 
+    // ---- wide-batch scan -------------------------------------------------------------------------------------
+    template <int CS, int MW> bool scan4_prepare_variant(int GC) {
+        const size_t smem = scan4::Cfg<CS, MW>::smem_bytes(d.H);
+        if (smem > 227 * 1024) return false;
+        if (cudaFuncSetAttribute(scan4::lstm_scan4_kernel<CS, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan4::Cfg<CS, MW>::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, scan4::lstm_scan4_kernel<CS, MW>, &cfg) != cudaSuccess || ncl * CS < GC) { cudaGetLastError(); return false; }   // every cluster must be co-resident
+        scan4_smem = smem;
+        return true;
+    }
+    template <int CS, int MW> void scan4_launch(const Scan4Layer& sl, const CUtensorMap& mh, const CUtensorMap& ml, const scan4::Args& a) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan4::Cfg<CS, MW>::THREADS); cfg.dynamicSmemBytes = scan4_smem; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        CK(cudaLaunchKernelEx(&cfg, scan4::lstm_scan4_kernel<CS, MW>, sl.mapW, mh, ml, a));
+    }
+
+    void init_scan4(const ModelWeights& w) {
+        const int D = d.D, H = d.H;
+        const char* sel = getenv("APRIL_B200_SCAN");
+        if (sel && strcmp(sel, "v4")) return;                              // an older kernel was asked for
+        if (H % 128 || H / scan4::UNITS > num_sms || D % 8) return;     // K slices are whole 64-wide k-blocks
+        const int GC = H / scan4::UNITS;
+        if (const char* e = getenv("APRIL_B200_SCAN_CS")) scan4_cs = atoi(e);
+        if (const char* e = getenv("APRIL_B200_SCAN_MMAW")) scan4_mmaw = atoi(e);
+        if (H % 256) scan4_cs = 2;
+        bool ok = false;
+        if (scan4_cs == 4 && scan4_mmaw == 1) ok = scan4_prepare_variant<4, 1>(GC);
+        else if (scan4_cs == 4) { scan4_mmaw = 2; ok = scan4_prepare_variant<4, 2>(GC); }
+        if (!ok) { scan4_cs = 2; if (scan4_mmaw != 2) scan4_mmaw = 4; ok = scan4_mmaw == 2 ? scan4_prepare_variant<2, 2>(GC) : scan4_prepare_variant<2, 4>(GC); }
+        if (!ok) return;
+        const int CS = scan4_cs, NC = 32 * CS, Kc = H / CS;
+        float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+        CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
+        std::vector<float> weff((size_t)4 * H * H);
+        for (auto& lw : w.layers) {
+            Scan4Layer sl;
+            CK(cudaMemcpy(dA, lw.w_hh.data(), sizeof(float) * (size_t)4 * H * D, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dB, lw.w_hr.data(), sizeof(float) * (size_t)D * H, cudaMemcpyHostToDevice));
+            scan4::weff_kernel<<<dim3((unsigned)((H + 15) / 16), (unsigned)((4 * H + 15) / 16)), 256, 0, st>>>(dA, dB, dC, 4 * H, H, D);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(weff.data(), dC, sizeof(float) * weff.size(), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const float sc = pow2_scale(weff, sl.inv);
+            CK(cudaMalloc(&sl.w, sizeof(__half) * (size_t)GC * 2 * NC * Kc)); owned.push_back(sl.w);
+            scan4::pack_weff_kernel<<<dim3((unsigned)GC, (unsigned)NC), 128, 0, st>>>(dC, sl.w, H, CS, sc);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 2 * NC, (uint64_t)Kc, 64, (uint32_t)NC, true);
+            sl.w_hr = make_tc_weight(lw.w_hr, D, H);
+            s4layers.push_back(sl);
+        }
+        CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
+        if (!scan_counters) { CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned))); owned.push_back(scan_counters); }
+        scan4 = true;
+    }
+
+    // one layer, steps [t0, t0+tc) of all B sessions of the pass: up to 512 sessions (4 groups of <= 128) per launch
+    void scan4_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
+        const int H = d.H;
+        const Scan4Layer& sl = s4layers[(size_t)l];
+        __half *Mh = b_mall_h.as<__half>(), *Ml = b_mall_l.as<__half>();
+        const size_t n0 = (size_t)B * H;
+        scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
+        static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
+        const int per_launch = scan4::MAXG * scan4::GROUP;
+        for (int g0 = 0; g0 < B; g0 += per_launch) {
+            const int Bc = std::min(per_launch, B - g0);
+            scan4::Args a{};
+            a.T = tc; a.t0 = t0;
+            a.NG = (Bc + scan4::GROUP - 1) / scan4::GROUP;
+            if (groups_env > a.NG && groups_env <= scan4::MAXG && Bc >= 8 * groups_env) a.NG = groups_env;
+            const int per = ((Bc + a.NG - 1) / a.NG + 7) & ~7;
+            for (int g = 0, o = 0; g < scan4::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::max(0, std::min(per, Bc - o)) : 0; o += a.Bg[g]; }
+            a.Bp = per;
+            a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan4::UNITS;
+            a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.G = G; a.c_state = cw; a.m_state = mw;
+            a.Mx_hi = Mh; a.Mx_lo = Ml; a.counter = scan_counters;
+            static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
+            const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
+            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
+            CK(cudaMemsetAsync(scan_counters, 0, 256 * sizeof(unsigned), st));
+            const CUtensorMap mh = make_map_f16(Mh, (uint64_t)(tc + 1) * B, (uint64_t)H, (uint32_t)a.Bp), ml = make_map_f16(Ml, (uint64_t)(tc + 1) * B, (uint64_t)H, (uint32_t)a.Bp);
+            if (scan4_cs == 4 && scan4_mmaw == 1) scan4_launch<4, 1>(sl, mh, ml, a);
+            else if (scan4_cs == 4) scan4_launch<4, 2>(sl, mh, ml, a);
+            else if (scan4_mmaw == 2) scan4_launch<2, 2>(sl, mh, ml, a);
+            else scan4_launch<2, 4>(sl, mh, ml, a);
+            launch_check();
+            if (do_trace) dump_trace(a.GC, tc, 1);
+        }
+    }
+
     // one layer, steps [t0, t0+tc): single-exchange scan; writes m rows (Mall) for the layer-output GEMM
     void scan2_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int H = d.H;
@@ -1002,8 +1109,10 @@ public:
             b_g.ensure(sizeof(float) * Mc * 4 * H); b_hout.ensure(sizeof(float) * Mc * D); b_f1.ensure(sizeof(float) * Mc * F);
             b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
             b_eo.ensure(sizeof(float) * Mc * J);
-            const bool use_s2 = npass && scan2;
-            if (use_s2) {
+            const bool use_s4 = npass && scan4;
+            const bool use_s2 = npass && (scan2 || scan4);
+            if (use_s4) { b_mall_h.ensure(sizeof(__half) * (Mc + (size_t)B) * H); b_mall_l.ensure(sizeof(__half) * (Mc + (size_t)B) * H); }
+            else if (use_s2) {
                 b_mx.ensure(sizeof(__half) * ((size_t)Tc + 1) * 2 * B * H); b_mall_h.ensure(sizeof(__half) * Mc * H); b_mall_l.ensure(sizeof(__half) * Mc * H);
             }
             b_mw.ensure(sizeof(float) * (size_t)L * B * H);
@@ -1053,7 +1162,8 @@ public:
                     float* hw = Hw + (size_t)l * B * D;
                     float* cw = Cw + (size_t)l * B * H;
                     span_begin(1);
-                    if (use_s2) scan2_layer(l, G, Mw + (size_t)l * B * H, cw, d_nsteps, t0, tc, B);
+                    if (use_s4) scan4_layer(l, G, Mw + (size_t)l * B * H, cw, d_nsteps, t0, tc, B);
+                    else if (use_s2) scan2_layer(l, G, Mw + (size_t)l * B * H, cw, d_nsteps, t0, tc, B);
                     else if (npass && scan_tc) scan_layer_tc(l, G, Hout, hw, cw, d_nsteps, t0, tc, B);
                     else for (int t = 0; t < tc; t++) {
                         k::lstm_gates_kernel<<<dim3((unsigned)(H / 16), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
@@ -1072,7 +1182,8 @@ public:
                         k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
                     } else {
                         const TcLayer& tl = tlayers[(size_t)l];
-                        if (use_s2) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>(), b_mall_l.as<__half>(), s2layers[(size_t)l].w_hr, nullptr, X, X1, X1_h, X1_l, M);   // x + W_hr m
+                        const size_t moff = use_s4 ? (size_t)B * H : 0;   // scan4: row block 0 of the m planes is the initial state
+                        if (use_s2) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>() + moff, b_mall_l.as<__half>() + moff, (use_s4 ? s4layers[(size_t)l].w_hr : s2layers[(size_t)l].w_hr), nullptr, X, X1, X1_h, X1_l, M);   // x + W_hr m
                         else { tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check(); }
                         gemm_tc(tc::GE_DSWISH_SPLIT, X1_h, X1_l, tl.ff1, w.ff1_b, nullptr, nullptr, F1_h, F1_l, M);
                         gemm_tc(tc::GE_F32_RESIDUAL, F1_h, F1_l, tl.ff2, w.ff2_b, X1, X2, nullptr, nullptr, M);
