@@ -39,7 +39,7 @@ TAP = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, cty
 class AprilB200Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("encoder_steps", "joiner_passes", "decoder_runs", "frames", "kernel_launches",
                                                "h2d_bytes", "d2h_bytes")] + \
-               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms", "compute_ms", "gemm_flops")] + [("gemm_launches", ctypes.c_uint64), ("greedy_ms", ctypes.c_double)]
+               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms", "compute_ms", "gemm_flops")] + [("gemm_launches", ctypes.c_uint64), ("greedy_ms", ctypes.c_double), ("passes", ctypes.c_uint64), ("pass_sessions", ctypes.c_uint64)]
 
 
 REFERENCE_SYMBOLS = [
@@ -48,7 +48,7 @@ REFERENCE_SYMBOLS = [
     "aas_realtime_get_speedup", "aas_free",
 ]
 B200_SYMBOLS = [
-    "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_get_stats",
+    "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_session_device", "aab_get_stats",
     "aab_set_tap", "aab_engine_version", "aab_debug_fbank", "aab_set_timing", "aab_counting_handler", "aab_debug_gemm", "aab_debug_replay", "aab_debug_plan",
 ]
 
@@ -81,6 +81,7 @@ class Lib:
             c.aab_flush_batch.argtypes, c.aab_flush_batch.restype = [ctypes.POINTER(vp), sz], ctypes.c_int
             c.aab_device_count.argtypes, c.aab_device_count.restype = [], ctypes.c_int
             c.aab_set_device.argtypes, c.aab_set_device.restype = [ctypes.c_int], ctypes.c_int
+            c.aab_session_device.argtypes, c.aab_session_device.restype = [ctypes.c_void_p], ctypes.c_int
             c.aab_engine_version.argtypes, c.aab_engine_version.restype = [], cp
             c.aab_debug_fbank.argtypes = [vp, ctypes.POINTER(ctypes.c_short), sz, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
             c.aab_debug_fbank.restype = ctypes.c_int

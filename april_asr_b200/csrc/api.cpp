@@ -2,7 +2,9 @@
 // april_b200.h. Session runtime semantics follow /root/reference/src/april_session.c (sync path
 // :479-564, async path :479-493,541-545,567-585 with src/audio_provider.c's 3 s ring) — the
 // forward path itself runs in the CUDA engine (engine.cu).
+#include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -37,13 +39,32 @@ static const char* kLevelNames[] = { "DEBUG", "INFO", "WARNING", "ERROR", "NONE"
 static const size_t kRingSamples = 48000;      // MAX_AUDIO, src/audio_provider.c:31
 
 struct AprilASRSession_i;
+struct AprilASRModel_i;
 
-struct AprilASRModel_i {
-    std::string name, description, language;
-    Params params;
-    Vocab vocab;
+struct SyncReq {                                 // one blocked aas_feed_pcm16 / aas_flush call of a synchronous session
+    AprilASRSession_i* s = nullptr;
+    PassItem item;
+    bool done = false;
+};
+
+// One GPU of a model: the engine (weights replicated per device) plus the two things that build batched passes
+// out of the reference's one-session-per-call API: the coalescer for synchronous callers and the batcher for async sessions.
+struct Lane {
+    AprilASRModel_i* model = nullptr;
+    int index = 0;
     std::unique_ptr<Engine> engine;
-    // per-GPU batcher for asynchronous sessions (replaces one ProcThread per session, src/proc_thread.c)
+    std::atomic<int> live_sessions{ 0 };
+    // synchronous callers (april-docs/src/concepts.md:41-58: many sessions of one model driven from many threads, each call
+    // blocking until its handler has run): calls that arrive while a pass is in flight, or within a short window of each
+    // other, are merged into ONE device pass by whichever caller becomes the leader; every caller then replays its own
+    // session's decisions (= invokes its handler) on its own thread before returning.
+    std::mutex qmu;
+    std::condition_variable qcv;
+    std::vector<SyncReq*> queue;
+    bool leader_active = false;
+    int live_sync = 0;                           // synchronous sessions placed on this lane
+    int miss_streak = 0;                         // consecutive windows that caught nobody
+    // asynchronous sessions: one batcher thread per GPU (replaces one ProcThread per session, src/proc_thread.c:138-172)
     std::mutex amu;
     std::condition_variable acv;
     std::vector<AprilASRSession_i*> async_sessions;
@@ -52,8 +73,18 @@ struct AprilASRModel_i {
     std::mutex pass_mu;                          // held while the batcher touches sessions
 };
 
+struct AprilASRModel_i {
+    std::string name, description, language;
+    Params params;
+    Vocab vocab;
+    std::vector<std::unique_ptr<Lane>> lanes;    // one per GPU this model runs on
+    std::mutex place_mu;
+    long coalesce_us = 100;
+};
+
 struct AprilASRSession_i {
     AprilASRModel_i* model = nullptr;
+    Lane* lane = nullptr;
     StreamFraming fr;
     std::unique_ptr<TokenShaper> shaper;
     AprilRecognitionResultHandler handler = nullptr;
@@ -61,15 +92,16 @@ struct AprilASRSession_i {
     bool sync = true;
     bool was_flushed = false;
     bool mismatch_reported = false;
-    // async input ring (guarded by model->amu)
+    // async input ring (guarded by lane->amu)
     std::vector<int16_t> ring;
     size_t ring_count = 0;
     bool flush_requested = false;
+    size_t flush_at = 0;                         // samples that were in the ring when the flush was requested: they go first
 };
 
 // ---------------------------------------------------------------------------------------------
 static void replay(AprilASRSession_i* s, PassItem& it, bool flush) {
-    const size_t stride = (size_t)s->model->engine->stride_ms();
+    const size_t stride = (size_t)s->lane->engine->stride_ms();
     for (int t = 0; t < it.n_steps; t++) {
         s->shaper->begin_step(stride);
         const int np = it.npass[(size_t)t];
@@ -85,19 +117,72 @@ static void replay(AprilASRSession_i* s, PassItem& it, bool flush) {
     if (flush) s->shaper->on_flush_end();
 }
 
-static void run_items(AprilASRModel_i* m, std::vector<AprilASRSession_i*>& ss, std::vector<PassItem>& items, bool flush) {
-    m->engine->run_pass(items);
-    for (size_t i = 0; i < ss.size(); i++) replay(ss[i], items[i], flush);
+// the batched entry points: sessions may live on different GPUs; each lane's pass runs concurrently, callbacks then run in index order
+static void run_items(std::vector<AprilASRSession_i*>& ss, std::vector<PassItem>& items) {
+    if (ss.empty()) return;
+    bool one_lane = true;
+    for (auto* s : ss) if (s->lane != ss[0]->lane) { one_lane = false; break; }
+    if (one_lane) ss[0]->lane->engine->run_pass(items);
+    else {
+        std::vector<Lane*> lanes;
+        for (auto* s : ss) if (std::find(lanes.begin(), lanes.end(), s->lane) == lanes.end()) lanes.push_back(s->lane);
+        std::vector<std::vector<PassItem>> per(lanes.size());
+        std::vector<std::vector<size_t>> idx(lanes.size());
+        for (size_t i = 0; i < ss.size(); i++) {
+            const size_t l = (size_t)(std::find(lanes.begin(), lanes.end(), ss[i]->lane) - lanes.begin());
+            per[l].push_back(std::move(items[i])); idx[l].push_back(i);
+        }
+        std::vector<std::thread> th;
+        for (size_t l = 0; l < lanes.size(); l++) th.emplace_back([&, l] { lanes[l]->engine->run_pass(per[l]); });
+        for (auto& t : th) t.join();
+        for (size_t l = 0; l < lanes.size(); l++) for (size_t k = 0; k < idx[l].size(); k++) items[idx[l][k]] = std::move(per[l][k]);
+    }
+    for (size_t i = 0; i < ss.size(); i++) replay(ss[i], items[i], items[i].flush);
 }
 
 // ---------------------------------------------------------------------------------------------
-static void batcher_main(AprilASRModel_i* m) {
+// synchronous call -> one request in the lane's queue; returns after this session's callbacks have run on this thread
+static void sync_submit(AprilASRSession_i* s, const int16_t* pcm, size_t count, bool flush) {
+    Lane& L = *s->lane;
+    SyncReq r;
+    r.s = s;
+    r.item.fr = &s->fr; r.item.cookie = s; r.item.pcm = pcm; r.item.count = count; r.item.flush = flush;
+    std::unique_lock<std::mutex> lk(L.qmu);
+    L.queue.push_back(&r);
+    if (L.leader_active) L.qcv.notify_all();                 // a leader inside its window may now have everybody
+    while (!r.done) {
+        if (L.leader_active) { L.qcv.wait(lk); continue; }
+        L.leader_active = true;                              // I lead: my request is in the queue, so it is part of my batch
+        const long win = L.model->coalesce_us;
+        if (win > 0 && (int)L.queue.size() < L.live_sync && L.miss_streak < 4) {
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(win);
+            while ((int)L.queue.size() < L.live_sync && L.qcv.wait_until(lk, deadline) != std::cv_status::timeout) {}
+        }
+        std::vector<SyncReq*> batch;
+        batch.swap(L.queue);
+        L.miss_streak = batch.size() > 1 ? 0 : std::min(L.miss_streak + 1, 1000);
+        if (L.miss_streak >= 4 && (L.miss_streak & 63) == 0) L.miss_streak = 0;        // probe again now and then
+        lk.unlock();
+        std::vector<PassItem> items(batch.size());
+        for (size_t i = 0; i < batch.size(); i++) items[i] = std::move(batch[i]->item);
+        L.engine->run_pass(items);
+        for (size_t i = 0; i < batch.size(); i++) batch[i]->item = std::move(items[i]);
+        lk.lock();
+        for (auto* b : batch) b->done = true;
+        L.leader_active = false;
+        L.qcv.notify_all();                                  // wakes my batch (done) and, if calls queued up meanwhile, the next leader
+    }
+    lk.unlock();
+    replay(s, r.item, flush);
+}
+
+// ---------------------------------------------------------------------------------------------
+static void batcher_main(Lane* m) {
     std::vector<AprilASRSession_i*> ss;
     std::vector<PassItem> items;
     std::vector<std::vector<int16_t>> chunks;
     for (;;) {
         ss.clear(); items.clear(); chunks.clear();
-        bool flush_pass = false;
         {
             std::unique_lock<std::mutex> lk(m->amu);
             m->acv.wait(lk, [&] {
@@ -109,29 +194,42 @@ static void batcher_main(AprilASRModel_i* m) {
         }
         std::unique_lock<std::mutex> pass_lk(m->pass_mu);     // lock order: pass_mu, then amu (aas_free does the same)
         {
+            // Decided per session (the reference has one thread per session, src/april_session.c:567-585): audio that was in
+            // the ring when a flush was requested goes first; a session whose flush is due is flushed in THIS pass whatever
+            // the other sessions are doing; audio fed after the flush request waits for the pass after it.
             std::unique_lock<std::mutex> lk(m->amu);
-            // audio first; sessions whose ring is empty and that asked for a flush are flushed next
-            for (auto* s : m->async_sessions) if (s->ring_count) {
-                ss.push_back(s);
-                chunks.emplace_back(s->ring.begin(), s->ring.begin() + (long)s->ring_count);
-                s->ring_count = 0;
+            for (auto* s : m->async_sessions) {
+                size_t take = s->ring_count;
+                if (s->flush_requested) take = std::min(take, s->flush_at);
+                if (take) {
+                    ss.push_back(s);
+                    chunks.emplace_back(s->ring.begin(), s->ring.begin() + (long)take);
+                    if (take < s->ring_count) memmove(s->ring.data(), s->ring.data() + take, (s->ring_count - take) * sizeof(int16_t));
+                    s->ring_count -= take;
+                    if (s->flush_requested) s->flush_at -= take;
+                    PassItem it; it.fr = &s->fr; it.cookie = s; it.pcm = chunks.back().data(); it.count = take;
+                    items.push_back(std::move(it));
+                    s->was_flushed = false;
+                } else if (s->flush_requested) {
+                    s->flush_requested = false;
+                    if (!s->was_flushed) {
+                        s->was_flushed = true;
+                        ss.push_back(s);
+                        chunks.emplace_back();
+                        PassItem it; it.fr = &s->fr; it.cookie = s; it.flush = true;
+                        items.push_back(std::move(it));
+                    }
+                }
             }
-            if (ss.empty()) {
-                flush_pass = true;
-                for (auto* s : m->async_sessions) if (s->flush_requested) { s->flush_requested = false; if (!s->was_flushed) { s->was_flushed = true; ss.push_back(s); } }
-            }
+            for (size_t i = 0; i < items.size(); i++) if (!items[i].flush) items[i].pcm = chunks[i].data();   // chunks may have reallocated
         }
         if (ss.empty()) continue;
-        items.resize(ss.size());
-        for (size_t i = 0; i < ss.size(); i++) {
-            items[i].fr = &ss[i]->fr; items[i].cookie = ss[i]; items[i].flush = flush_pass;
-            if (!flush_pass) { items[i].pcm = chunks[i].data(); items[i].count = chunks[i].size(); ss[i]->was_flushed = false; }
-        }
-        run_items(m, ss, items, flush_pass);
+        m->engine->run_pass(items);
+        for (size_t i = 0; i < ss.size(); i++) replay(ss[i], items[i], items[i].flush);
     }
 }
 
-static void ensure_batcher(AprilASRModel_i* m) {
+static void ensure_batcher(Lane* m) {
     std::lock_guard<std::mutex> lk(m->amu);
     if (!m->batcher_started) { m->batcher_started = true; m->batcher = std::thread(batcher_main, m); }
 }
@@ -146,23 +244,32 @@ APRIL_EXPORT void aam_api_init(int version) {
     g_initialized = 1;
 }
 
-APRIL_EXPORT int aab_device_count(void) { return cuda_device_count_sm100(); }
+APRIL_EXPORT int aab_device_count(void) { return (int)cuda_devices_sm100().size(); }
 
 APRIL_EXPORT int aab_set_device(int device) {
-    if (device < 0 || device >= cuda_device_count_sm100()) return -1;
-    tl_device = device;
+    if (device < -1 || device >= (int)cuda_devices_sm100().size()) return -1;
+    tl_device = device;                                      // -1: back to the default (all visible B200s)
     return 0;
 }
 
-APRIL_EXPORT const char* aab_engine_version(void) { return "april-b200 r1b (sm_100a; exact fp32 tier + tcgen05 tier: pair GEMMs, single-exchange K-split scan)"; }
+APRIL_EXPORT const char* aab_engine_version(void) { return "april-b200 r2 (sm_100a; tcgen05 tier: pair GEMMs, wide-batch K-split scan; per-GPU lanes with sync-call coalescing)"; }
 
-static int pick_device() {
-    if (tl_device >= 0) return tl_device;
-    const char* e = getenv("APRIL_B200_DEVICE");
-    if (!e) e = getenv("LOCAL_RANK");
-    int n = cuda_device_count_sm100();
-    if (e && n > 0) { int v = atoi(e); if (v >= 0) return v % n; }
-    return 0;
+// CUDA ordinals this model should run on. A pinned device (aab_set_device on this thread, APRIL_B200_DEVICE, or LOCAL_RANK under
+// torchrun: one process per GPU) gives one lane; otherwise every visible sm_100 device gets an engine and sessions are placed
+// on the least-loaded one (the reference has no device notion: src/april_session.c:25-93).
+static std::vector<int> pick_devices() {
+    const std::vector<int> all = cuda_devices_sm100();       // index among B200s -> CUDA ordinal
+    if (all.empty()) return all;
+    int pin = tl_device;
+    if (pin < 0) {
+        const char* e = getenv("APRIL_B200_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        if (e && *e) { const int v = atoi(e); if (v >= 0) pin = v % (int)all.size(); }
+    }
+    if (pin >= 0) return { all[(size_t)pin] };
+    std::vector<int> out = all;
+    if (const char* e = getenv("APRIL_B200_MAX_DEVICES")) { const int n = atoi(e); if (n > 0 && (size_t)n < out.size()) out.resize((size_t)n); }
+    return out;
 }
 
 APRIL_EXPORT AprilASRModel aam_create_model(const char* model_path) {
@@ -176,10 +283,23 @@ APRIL_EXPORT AprilASRModel aam_create_model(const char* model_path) {
     m->params = lm.params;
     m->vocab.tokens = lm.params.tokens;
     m->vocab.blank_id = lm.params.blank_id;
-    Engine* e = Engine::create(lm, pick_device(), err);
-    if (!e) { LOG_ERROR("aam: cannot create the B200 engine: %s", err.c_str()); return nullptr; }
-    m->engine.reset(e);
-    LOG_INFO("aam: loaded model %s on cuda:%d", m->name.c_str(), e->device());
+    if (const char* e = getenv("APRIL_B200_COALESCE_US")) m->coalesce_us = atol(e);
+    const std::vector<int> devs = pick_devices();
+    if (devs.empty()) { LOG_ERROR("aam: no sm_100 (B200) device available; this library has no CPU fallback"); return nullptr; }
+    std::vector<std::string> errs(devs.size());
+    m->lanes.resize(devs.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < devs.size(); i++)
+        th.emplace_back([&, i] {
+            std::unique_ptr<Lane> L(new Lane());
+            L->model = m.get(); L->index = (int)i;
+            L->engine.reset(Engine::create(lm, devs[i], errs[i]));
+            if (L->engine) m->lanes[i] = std::move(L);
+        });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < devs.size(); i++)
+        if (!m->lanes[i]) { LOG_ERROR("aam: cannot create the B200 engine on cuda:%d: %s", devs[i], errs[i].c_str()); return nullptr; }
+    LOG_INFO("aam: loaded model %s on %d GPU(s), first cuda:%d", m->name.c_str(), (int)devs.size(), devs[0]);
     return m.release();
 }
 
@@ -190,12 +310,14 @@ APRIL_EXPORT size_t aam_get_sample_rate(AprilASRModel model) { return (size_t)mo
 
 APRIL_EXPORT void aam_free(AprilASRModel model) {
     if (!model) return;
-    {
-        std::lock_guard<std::mutex> lk(model->amu);
-        model->stop = true;
+    for (auto& L : model->lanes) {
+        {
+            std::lock_guard<std::mutex> lk(L->amu);
+            L->stop = true;
+        }
+        L->acv.notify_all();
+        if (L->batcher_started) L->batcher.join();
     }
-    model->acv.notify_all();
-    if (model->batcher_started) model->batcher.join();
     delete model;
 }
 
@@ -208,12 +330,23 @@ APRIL_EXPORT AprilASRSession aas_create_session(AprilASRModel model, AprilConfig
     s->handler = config.handler;
     s->userdata = config.userdata;
     s->shaper.reset(new TokenShaper(&model->vocab, config.handler, config.userdata));
-    s->fr.slot = model->engine->alloc_slot();
+    {
+        std::lock_guard<std::mutex> lk(model->place_mu);     // least-loaded GPU; ties go to the lowest index
+        Lane* best = model->lanes[0].get();
+        for (auto& L : model->lanes) if (L->live_sessions.load() < best->live_sessions.load()) best = L.get();
+        s->lane = best;
+        best->live_sessions++;
+    }
+    Lane* L = s->lane;
+    s->fr.slot = L->engine->alloc_slot();
     if (!s->sync) {
         s->ring.resize(kRingSamples);
-        ensure_batcher(model);
-        std::lock_guard<std::mutex> lk(model->amu);
-        model->async_sessions.push_back(s.get());
+        ensure_batcher(L);
+        std::lock_guard<std::mutex> lk(L->amu);
+        L->async_sessions.push_back(s.get());
+    } else {
+        std::lock_guard<std::mutex> lk(L->qmu);
+        L->live_sync++;
     }
     return s.release();
 }
@@ -222,27 +355,29 @@ APRIL_EXPORT float aas_realtime_get_speedup(AprilASRSession session) { (void)ses
 
 APRIL_EXPORT void aas_free(AprilASRSession session) {
     if (!session) return;
-    AprilASRModel_i* m = session->model;
+    Lane* m = session->lane;
     if (!session->sync) {
         std::lock_guard<std::mutex> pl(m->pass_mu);       // wait for an in-flight batcher pass
         std::lock_guard<std::mutex> lk(m->amu);
         auto& v = m->async_sessions;
         for (size_t i = 0; i < v.size(); i++) if (v[i] == session) { v.erase(v.begin() + (long)i); break; }
+    } else {
+        std::lock_guard<std::mutex> lk(m->qmu);
+        m->live_sync--;
+        m->qcv.notify_all();                              // a leader waiting for "everybody" re-evaluates
     }
     m->engine->free_slot(session->fr.slot);
+    m->live_sessions--;
     delete session;
 }
 
 APRIL_EXPORT void aas_feed_pcm16(AprilASRSession session, short* pcm16, size_t short_count) {
     if (!session) return;
-    AprilASRModel_i* m = session->model;
+    Lane* m = session->lane;
     if (session->sync) {
         session->was_flushed = false;                                   // april_session.c:510
         if (short_count == 0 || !pcm16) return;
-        std::vector<AprilASRSession_i*> ss{ session };
-        std::vector<PassItem> items(1);
-        items[0].fr = &session->fr; items[0].cookie = session; items[0].pcm = pcm16; items[0].count = short_count;
-        run_items(m, ss, items, false);
+        sync_submit(session, pcm16, short_count, false);
         return;
     }
     bool ok = true;
@@ -257,19 +392,16 @@ APRIL_EXPORT void aas_feed_pcm16(AprilASRSession session, short* pcm16, size_t s
 
 APRIL_EXPORT void aas_flush(AprilASRSession session) {
     if (!session) return;
-    AprilASRModel_i* m = session->model;
+    Lane* m = session->lane;
     if (session->sync) {
         if (session->was_flushed) return;                               // april_session.c:548-550
         session->was_flushed = true;
-        std::vector<AprilASRSession_i*> ss{ session };
-        std::vector<PassItem> items(1);
-        items[0].fr = &session->fr; items[0].cookie = session; items[0].flush = true;
-        run_items(m, ss, items, true);
+        sync_submit(session, nullptr, 0, true);
         return;
     }
     {
         std::lock_guard<std::mutex> lk(m->amu);
-        session->flush_requested = true;
+        if (!session->flush_requested) { session->flush_requested = true; session->flush_at = session->ring_count; }
     }
     m->acv.notify_one();
 }
@@ -297,7 +429,7 @@ APRIL_EXPORT int aab_feed_pcm16_batch(AprilASRSession* sessions, short** pcm16, 
         PassItem it; it.fr = &sessions[i]->fr; it.cookie = sessions[i]; it.pcm = pcm16[i]; it.count = short_count[i];
         items.push_back(std::move(it));
     }
-    if (!ss.empty()) run_items(sessions[0]->model, ss, items, false);
+    run_items(ss, items);
     return 0;
 }
 
@@ -312,25 +444,31 @@ APRIL_EXPORT int aab_flush_batch(AprilASRSession* sessions, size_t n) {
         PassItem it; it.fr = &sessions[i]->fr; it.cookie = sessions[i]; it.flush = true;
         items.push_back(std::move(it));
     }
-    if (!ss.empty()) run_items(sessions[0]->model, ss, items, true);
+    run_items(ss, items);
     return 0;
 }
+
+APRIL_EXPORT int aab_session_device(AprilASRSession session) { return session ? session->lane->engine->device() : -1; }
 
 APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int reset) {
     if (!model || !out) return -1;
-    EngineStats s = model->engine->stats(reset != 0);
-    out->encoder_steps = s.encoder_steps; out->joiner_passes = s.joiner_passes; out->decoder_runs = s.decoder_runs; out->frames = s.frames;
-    out->kernel_launches = s.kernel_launches; out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
-    out->device_ms = s.device_ms; out->lstm_scan_ms = s.lstm_scan_ms; out->gemm_ms = s.gemm_ms;
-    out->compute_ms = s.compute_ms; out->gemm_flops = s.gemm_flops; out->gemm_launches = s.gemm_launches; out->greedy_ms = s.greedy_ms;
+    memset(out, 0, sizeof *out);
+    for (auto& L : model->lanes) {                          // summed over the model's GPUs (times: the slowest lane)
+        EngineStats s = L->engine->stats(reset != 0);
+        out->encoder_steps += s.encoder_steps; out->joiner_passes += s.joiner_passes; out->decoder_runs += s.decoder_runs; out->frames += s.frames;
+        out->kernel_launches += s.kernel_launches; out->h2d_bytes += s.h2d_bytes; out->d2h_bytes += s.d2h_bytes;
+        out->gemm_flops += s.gemm_flops; out->gemm_launches += s.gemm_launches; out->passes += s.passes; out->pass_sessions += s.pass_sessions;
+        out->device_ms = std::max(out->device_ms, s.device_ms); out->lstm_scan_ms = std::max(out->lstm_scan_ms, s.lstm_scan_ms); out->gemm_ms = std::max(out->gemm_ms, s.gemm_ms);
+        out->compute_ms = std::max(out->compute_ms, s.compute_ms); out->greedy_ms = std::max(out->greedy_ms, s.greedy_ms);
+    }
     return 0;
 }
 
-APRIL_EXPORT void aab_set_timing(AprilASRModel model, int enabled) { if (model) model->engine->set_timing(enabled != 0); }
+APRIL_EXPORT void aab_set_timing(AprilASRModel model, int enabled) { if (model) for (auto& L : model->lanes) L->engine->set_timing(enabled != 0); }
 
 APRIL_EXPORT void aab_set_tap(AprilASRModel model, AprilB200Tap tap, void* userdata) {
     if (!model) return;
-    model->engine->set_tap(reinterpret_cast<TapFn>(tap), userdata);
+    for (auto& L : model->lanes) L->engine->set_tap(reinterpret_cast<TapFn>(tap), userdata);
 }
 
 // A ready-made handler for throughput measurements: userdata points at 4 uint64 counters
@@ -346,12 +484,12 @@ APRIL_EXPORT void aab_counting_handler(void* userdata, AprilResultType type, siz
 
 APRIL_EXPORT int aab_debug_fbank(AprilASRModel model, const short* pcm16, size_t short_count, float* out_rows, int max_rows) {
     if (!model || !pcm16 || !out_rows) return -1;
-    return model->engine->debug_fbank(pcm16, short_count, out_rows, max_rows);
+    return model->lanes[0]->engine->debug_fbank(pcm16, short_count, out_rows, max_rows);
 }
 
 APRIL_EXPORT int aab_debug_gemm(AprilASRModel model, int tier, int M, int N, int K, const float* A, const float* W, const float* bias, float* out) {
     if (!model || !A || !W || !bias || !out) return -1;
-    return model->engine->debug_gemm(tier, M, N, K, A, W, bias, out);
+    return model->lanes[0]->engine->debug_gemm(tier, M, N, K, A, W, bias, out);
 }
 
 APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_records, const int* max_idx, const float* max_val, const float* blank_val,

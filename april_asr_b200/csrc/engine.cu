@@ -996,6 +996,7 @@ public:
         std::lock_guard<std::mutex> lk(mu);
         const int B = (int)items.size();
         if (B == 0) return;
+        stat.passes++; stat.pass_sessions += (uint64_t)B;
         CK(cudaSetDevice(dev));
         const int SEG = d.SEG, STEP = d.STEP, N = frame_N, shift = frame_shift, MEL = d.MEL;
 
@@ -1282,12 +1283,12 @@ Engine* Engine::create(const LoadedModel& m, int device, std::string& err) {
     return e;
 }
 
-int cuda_device_count_sm100() {
+std::vector<int> cuda_devices_sm100() {
+    std::vector<int> out;
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-    int ok = 0;
-    for (int i = 0; i < n; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++; }
-    return ok;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return out; }
+    for (int i = 0; i < n; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) out.push_back(i); }
+    return out;
 }
 
 }  // namespace april

@@ -47,6 +47,7 @@ struct EngineStats {
     double device_ms = 0, lstm_scan_ms = 0, gemm_ms = 0, compute_ms = 0, gemm_flops = 0;
     uint64_t gemm_launches = 0;
     double greedy_ms = 0;
+    uint64_t passes = 0, pass_sessions = 0;
 };
 
 typedef void (*TapFn)(void* userdata, void* cookie, int net, const float* data, size_t n);
@@ -68,6 +69,6 @@ public:
     virtual int device() const = 0;
 };
 
-int cuda_device_count_sm100();
+std::vector<int> cuda_devices_sm100();     // CUDA ordinals of the usable sm_100 devices, in ordinal order
 
 }  // namespace april

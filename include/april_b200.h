@@ -35,9 +35,15 @@ APRIL_EXPORT int aab_flush_batch(AprilASRSession* sessions, size_t n_sessions);
 /* Number of usable sm_100 devices; 0 means the library cannot run (there is no CPU fallback). */
 APRIL_EXPORT int aab_device_count(void);
 
-/* Select the CUDA device used by models created afterwards on this thread's behalf (default: env
- * APRIL_B200_DEVICE, else LOCAL_RANK, else 0). Sessions inherit their model's device. */
+/* Device placement (the reference has no device notion, src/april_session.c:25-93). By default
+ * aam_create_model builds one engine per visible sm_100 device (weights replicated) and aas_create_session places each new
+ * session on the least-loaded one: a drop-in C caller on an 8-GPU box uses all eight. One process per GPU (torchrun) is the
+ * other supported layout: LOCAL_RANK or APRIL_B200_DEVICE pins every model of the process to that B200 (index among the
+ * sm_100 devices, mapped to the CUDA ordinal internally), and aab_set_device(i) pins the models created afterwards on the
+ * calling thread; aab_set_device(-1) returns to the default. APRIL_B200_MAX_DEVICES caps the number of engines. */
 APRIL_EXPORT int aab_set_device(int device);
+/* CUDA ordinal of the GPU a session was placed on. */
+APRIL_EXPORT int aab_session_device(AprilASRSession session);
 
 typedef struct AprilB200Stats {
     uint64_t encoder_steps;     /* session-steps run through the encoder */
@@ -54,6 +60,8 @@ typedef struct AprilB200Stats {
     double   gemm_flops;        /* algorithmic FLOPs (2 M N K) of the GEMM launches timed in gemm_ms */
     uint64_t gemm_launches;
     double   greedy_ms;         /* ... of which the joiner + greedy search kernel */
+    uint64_t passes;            /* batched device passes run */
+    uint64_t pass_sessions;     /* sessions summed over those passes (pass_sessions / passes = mean batch) */
 } AprilB200Stats;
 
 /* Cumulative statistics of a model's engine; reset != 0 zeroes them after reading. lstm_scan_ms / gemm_ms /
