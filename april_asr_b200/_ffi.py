@@ -39,7 +39,8 @@ TAP = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, cty
 class AprilB200Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("encoder_steps", "joiner_passes", "decoder_runs", "frames", "kernel_launches",
                                                "h2d_bytes", "d2h_bytes")] + \
-               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms", "compute_ms", "gemm_flops")] + [("gemm_launches", ctypes.c_uint64), ("greedy_ms", ctypes.c_double), ("passes", ctypes.c_uint64), ("pass_sessions", ctypes.c_uint64)]
+               [(n, ctypes.c_double) for n in ("device_ms", "lstm_scan_ms", "gemm_ms", "compute_ms", "gemm_flops")] + [("gemm_launches", ctypes.c_uint64), ("greedy_ms", ctypes.c_double), ("passes", ctypes.c_uint64), ("pass_sessions", ctypes.c_uint64),
+                  ("lstm_gemm_ms", ctypes.c_double), ("lstm_gemm_flops", ctypes.c_double), ("frontend_ms", ctypes.c_double)]
 
 
 REFERENCE_SYMBOLS = [

@@ -383,7 +383,7 @@ APRIL_EXPORT void aas_feed_pcm16(AprilASRSession session, short* pcm16, size_t s
     bool ok = true;
     {
         std::lock_guard<std::mutex> lk(m->amu);
-        if (session->ring_count + short_count > kRingSamples) ok = false;    // ap_push_audio, src/audio_provider.c:59-64: drop the chunk
+        if (session->ring_count + short_count >= kRingSamples) ok = false;   // ap_push_audio, src/audio_provider.c:59-64 (>=): drop the whole chunk
         else { memcpy(session->ring.data() + session->ring_count, pcm16, short_count * sizeof(int16_t)); session->ring_count += short_count; }
     }
     m->acv.notify_one();
@@ -457,7 +457,8 @@ APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int res
         EngineStats s = L->engine->stats(reset != 0);
         out->encoder_steps += s.encoder_steps; out->joiner_passes += s.joiner_passes; out->decoder_runs += s.decoder_runs; out->frames += s.frames;
         out->kernel_launches += s.kernel_launches; out->h2d_bytes += s.h2d_bytes; out->d2h_bytes += s.d2h_bytes;
-        out->gemm_flops += s.gemm_flops; out->gemm_launches += s.gemm_launches; out->passes += s.passes; out->pass_sessions += s.pass_sessions;
+        out->gemm_flops += s.gemm_flops; out->gemm_launches += s.gemm_launches; out->passes += s.passes; out->pass_sessions += s.pass_sessions; out->lstm_gemm_flops += s.lstm_gemm_flops;
+        out->lstm_gemm_ms = std::max(out->lstm_gemm_ms, s.lstm_gemm_ms); out->frontend_ms = std::max(out->frontend_ms, s.frontend_ms);
         out->device_ms = std::max(out->device_ms, s.device_ms); out->lstm_scan_ms = std::max(out->lstm_scan_ms, s.lstm_scan_ms); out->gemm_ms = std::max(out->gemm_ms, s.gemm_ms);
         out->compute_ms = std::max(out->compute_ms, s.compute_ms); out->greedy_ms = std::max(out->greedy_ms, s.greedy_ms);
     }

@@ -192,7 +192,7 @@ public:
     void span_begin(int cls) { if (!profile) return; Span sp{ ev_get(), ev_get(), cls }; CK(cudaEventRecord(sp.a, st)); spans.push_back(sp); }
     void span_end() { if (!profile) return; CK(cudaEventRecord(spans.back().b, st)); }
     void spans_collect() {
-        for (auto& sp : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, sp.a, sp.b)); (sp.cls == 0 ? stat.gemm_ms : (sp.cls == 1 ? stat.lstm_scan_ms : stat.greedy_ms)) += ms; ev_pool.push_back(sp.a); ev_pool.push_back(sp.b); }
+        for (auto& sp : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, sp.a, sp.b)); if (sp.cls == 0) stat.gemm_ms += ms; else if (sp.cls == 1) stat.lstm_scan_ms += ms; else if (sp.cls == 2) stat.greedy_ms += ms; else if (sp.cls == 3) { stat.gemm_ms += ms; stat.lstm_gemm_ms += ms; } else stat.frontend_ms += ms; ev_pool.push_back(sp.a); ev_pool.push_back(sp.b); }
         spans.clear();
     }
 
@@ -321,8 +321,11 @@ public:
                 tlayers.push_back(tl);
             }
             set_gemm_attrs();
-            init_scan4(w);
-            if (!scan4) { init_scan(w); init_scan2(w); }
+            const char* scan_sel = getenv("APRIL_B200_SCAN");
+            if (!(scan_sel && !strcmp(scan_sel, "simt"))) {          // "simt": per-step fp32 recurrence inside the tensor-core tier (precision studies)
+                init_scan4(w);
+                if (!scan4) { init_scan(w); init_scan2(w); }
+            }
         }
 
         // vocabulary flags (april_session.c:338-351)
@@ -893,9 +896,9 @@ public:
 
     // C = A * W^T (+bias, epilogue) on the tensor cores. A given as fp16 (hi, lo) [M, K].
     void gemm_tc(int epi, const __half* a_hi, const __half* a_lo, const TcWeight& w, const float* bias, const float* residual,
-                 float* out_f32, __half* out_hi, __half* out_lo, int M) {
-        span_begin(0);
-        if (profile) { stat.gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; stat.gemm_launches++; }
+                 float* out_f32, __half* out_hi, __half* out_lo, int M, int cls = 0) {
+        span_begin(cls);
+        if (profile) { stat.gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; stat.gemm_launches++; if (cls == 3) stat.lstm_gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; }
         static const bool pair_env = getenv("APRIL_B200_GEMM_CLUSTER") == nullptr || atoi(getenv("APRIL_B200_GEMM_CLUSTER")) != 1;
         const int tiles_m = (M + tc::GEMM_BM - 1) / tc::GEMM_BM, tiles_n = (w.N + tc::GEMM_BN - 1) / tc::GEMM_BN;
         const bool pair = pair_env && tiles_m >= 2;          // CTA pairs (cta_group::2): each CTA ingests its A rows and half of the B rows
@@ -1086,6 +1089,7 @@ public:
         // ---- front-end ------------------------------------------------------------------------------
         b_fb.ensure(sizeof(float) * (size_t)B * row_pitch * MEL);
         float* FB = b_fb.as<float>();
+        span_begin(4);
         k::carry_in_kernel<<<B, 128, 0, st>>>(carry_store, d_slot, d_carry, FB, row_pitch, MEL, CARRY_CAP); launch_check();
         if (max_new > 0) {
             if (fbank_v2()) {
@@ -1097,6 +1101,7 @@ public:
             }
             launch_check();
         }
+        span_end();
 
         // ---- encoder + search, in time chunks -------------------------------------------------------
         size_t rec_bytes = 0, np_bytes = 0;
@@ -1159,7 +1164,7 @@ public:
                 for (int l = 0; l < L; l++) {
                     const DeviceLayer& w = layers[(size_t)l];
                     if (npass == 0) gemm(k::EPI_BIAS, X, w.w_ih, w.b_gate, nullptr, G, M, 4 * H, D);
-                    else gemm_tc(tc::GE_F32, X_h, X_l, tlayers[(size_t)l].w_ih, w.b_gate, nullptr, G, nullptr, nullptr, M);
+                    else gemm_tc(tc::GE_F32, X_h, X_l, tlayers[(size_t)l].w_ih, w.b_gate, nullptr, G, nullptr, nullptr, M, 3);
                     float* hw = Hw + (size_t)l * B * D;
                     float* cw = Cw + (size_t)l * B * H;
                     span_begin(1);
@@ -1184,7 +1189,7 @@ public:
                     } else {
                         const TcLayer& tl = tlayers[(size_t)l];
                         const size_t moff = use_s4 ? (size_t)B * H : 0;   // scan4: row block 0 of the m planes is the initial state
-                        if (use_s2) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>() + moff, b_mall_l.as<__half>() + moff, (use_s4 ? s4layers[(size_t)l].w_hr : s2layers[(size_t)l].w_hr), nullptr, X, X1, X1_h, X1_l, M);   // x + W_hr m
+                        if (use_s2) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>() + moff, b_mall_l.as<__half>() + moff, (use_s4 ? s4layers[(size_t)l].w_hr : s2layers[(size_t)l].w_hr), nullptr, X, X1, X1_h, X1_l, M, 3);   // x + W_hr m
                         else { tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check(); }
                         gemm_tc(tc::GE_DSWISH_SPLIT, X1_h, X1_l, tl.ff1, w.ff1_b, nullptr, nullptr, F1_h, F1_l, M);
                         gemm_tc(tc::GE_F32_RESIDUAL, F1_h, F1_l, tl.ff2, w.ff2_b, X1, X2, nullptr, nullptr, M);

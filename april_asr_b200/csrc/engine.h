@@ -48,6 +48,8 @@ struct EngineStats {
     uint64_t gemm_launches = 0;
     double greedy_ms = 0;
     uint64_t passes = 0, pass_sessions = 0;
+    double lstm_gemm_ms = 0, lstm_gemm_flops = 0;   // the W_ih and W_hr (layer output) GEMMs: with lstm_scan_ms, the LSTM-GEMM subset of north_star
+    double frontend_ms = 0;                          // fbank + carry rows
 };
 
 typedef void (*TapFn)(void* userdata, void* cookie, int net, const float* data, size_t n);

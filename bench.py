@@ -1,13 +1,17 @@
 #!/usr/bin/env python3
-"""bench.py — audio frames/s of the batched RNN-T hot path (fbank -> encoder -> decoder/joiner ->
-greedy search) behind the april C ABI, on N B200s (one process per GPU, sessions sharded, no collective
-on the data path), next to the reference's CPU path.
+"""bench.py — audio frames/s of the batched RNN-T hot path (fbank -> encoder -> decoder/joiner -> greedy search) behind the
+april C ABI, on N B200s (one process per GPU, sessions sharded, no collective on the data path), next to the reference's
+CPU path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--sessions S] [--seconds T]
 
-One "step" = one pass of the hot path over one batch: `sessions` fresh streams of `seconds` of synthetic
-16 kHz s16 PCM are fed whole (aab_feed_pcm16_batch) and flushed (aab_flush_batch) — BASELINE.json
-configs[1] at N=1 (64 x 30 s), configs[2] sharded 64 per GPU at N>1.
+One "step" = one pass of the hot path over one batch: `sessions` fresh streams of `seconds` of synthetic 16 kHz s16 PCM are
+fed whole (aab_feed_pcm16_batch) and flushed (aab_flush_batch) — BASELINE.json configs[1] at N=1 (64 x 30 s), configs[2]
+sharded 64 per GPU at N>1. The default line also carries, as extra blocks measured in the same process after the timed steps:
+  "b512":     512 sessions x 30 s on this GPU (north_star's operating point),
+  "stream":   configs[3] — 256 synchronous sessions, one native thread each, 40 ms chunks through plain aas_feed_pcm16
+              (coalesced into batched passes inside the library), p50/p99 of the per-chunk latency,
+  "cpu_baseline": the reference's own host code on this box's cores.
 """
 import argparse
 import ctypes
@@ -17,7 +21,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -27,15 +30,52 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 FRAMES_PER_STREAM = lambda n: (n - 512) // 160 + 1          # frames = floor((N-512)/160)+1
-FLOP_PER_STEP_ENCODER = 2.0 * 84_196_240
+FLOP_PER_STEP_ENCODER = 2.0 * 84_196_240                    # BASELINE.md §2 / SURVEY.md §8d
+FLOP_PER_STEP_LSTM_GEMM = 2.0 * 12 * 4_718_592              # W_ih + W_hh + W_hr of the 12 layers: the subset north_star's >= 50 % refers to
+FLOP_PER_STEP_RECURRENT = 2.0 * 12 * (4096 * 512 + 512 * 1024)   # W_hh + W_hr: what the scan kernel replaces, counted as the reference computes it
+ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "libaprilasr_ref.so")
+
+
+def steps_of_clip(n_samples):
+    """Encoder steps the reference runs for one clip fed whole and flushed (plan.h restates it)."""
+    frames = FRAMES_PER_STREAM(n_samples)
+    feed = max(0, (frames - 9) // 4 + 1)
+    return feed + 28
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def ncu_traffic(kernel_substr):
+    """dram bytes read + written by one launch of the dominant kernel, from the newest committed `ncu --set full` raw page of it
+    under profiles/ (per launch); None when there is no capture of the current kernel."""
+    import csv, glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*.raw.csv"))):
+        try:
+            rows = list(csv.reader(open(f)))
+        except Exception:
+            continue
+        if len(rows) < 3:
+            continue
+        hdr = rows[0]
+        try:
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        units = rows[1]
+        scale = lambda u: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+        for r in rows[2:]:
+            if len(r) > max(ik, ir, iw) and kernel_substr in r[ik]:
+                try:
+                    best = {"bytes": float(r[ir].replace(",", "")) * scale(units[ir]) + float(r[iw].replace(",", "")) * scale(units[iw]), "file": os.path.relpath(f, ROOT)}
+                except ValueError:
+                    pass
+    return best
 
 
 class ClockSampler:
@@ -86,42 +126,55 @@ def ensure_model(rank, dist):
     return path
 
 
-def time_cpu_reference(model_path, seconds_per_session, n_threads, first_id=0):
-    """The reference's own host code (oracle/_ref: /root/reference/src/*.c compiled unmodified over the CPU
-    fp32 ONNX interpreter), one OS thread per session like the reference (1 intra-op thread,
-    april_model.c:54-55). Returns (frames/s, wall s, frames)."""
-    import april_asr_b200 as A
-    from gen_pcm import gen_stream
-    so = os.path.join(ROOT, "oracle", "_ref", "libaprilasr_ref.so")
-    lib = A.Lib(so)
-    m = A.Model(model_path, lib)
-    n = int(16000 * seconds_per_session)
-    pcms = [gen_stream(first_id + i, n) for i in range(n_threads)]
-    counters = [(ctypes.c_uint64 * 4)() for _ in range(n_threads)]
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own host code (oracle/_ref: /root/reference/src/*.c compiled unmodified over the CPU fp32 ONNX
+# interpreter), one native thread per session like the reference (1 intra-op thread, april_model.c:54-55), driven through
+# aas_feed_pcm16 + aas_flush by tools/stream_driver.cpp. A step of the reference costs the same whatever the clip (fixed-size
+# graphs, batch 1), so a bounded sample is scaled to the benchmarked clip BY ENCODER STEPS: the flush tail (28 steps) weighs
+# in the reported value exactly as it does in a 30 s clip, whatever the sample's own length.
+# ------------------------------------------------------------------------------------------------------------------
+class CpuArm:
+    def __init__(self, model_path):
+        import april_asr_b200 as A
+        import stream_driver as SD
+        from gen_pcm import gen_stream
+        self.A, self.SD, self.gen = A, SD, gen_stream
+        self.lib = A.Lib(ORACLE_SO)
+        self.lib.c.fake_ort_get_run_counts.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+        self.m = A.Model(model_path, self.lib)
 
-    def _noop(ud, r, cnt, toks):
-        return None
-    handler = A.HANDLER(_noop)
-    sessions = []
-    for i in range(n_threads):
-        cfg = A.AprilConfig(); cfg.handler = handler; cfg.userdata = None; cfg.flags = 0
-        sessions.append(lib.c.aas_create_session(m.handle, cfg))
+    def enc_runs(self):
+        c = (ctypes.c_uint64 * 3)()
+        self.lib.c.fake_ort_get_run_counts(c)
+        return int(c[0])
 
-    def work(i):
-        lib.c.aas_feed_pcm16(sessions[i], pcms[i].ctypes.data_as(ctypes.POINTER(ctypes.c_short)), pcms[i].size)
-        lib.c.aas_flush(sessions[i])
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    wall = time.perf_counter() - t0
-    for s in sessions:
-        lib.c.aas_free(s)
-    m.close()
-    frames = n_threads * FRAMES_PER_STREAM(n)
-    return frames / wall, wall, frames
+    def sample(self, n_threads, seconds, first_id=0):
+        """n_threads sessions x `seconds` fed whole + flushed. Returns (wall s, encoder steps run)."""
+        n = int(16000 * seconds)
+        pcms = [self.gen(first_id + i, n) for i in range(n_threads)]
+        r0 = self.enc_runs()
+        wall_ms, _ = self.SD.bulk(self.lib, self.m.handle, pcms, 0)
+        return wall_ms / 1e3, self.enc_runs() - r0
+
+    def measure(self, n_threads, budget_s, clip_seconds, first_id=0):
+        """Calibrates on a 0.5 s clip, then times ONE sample sized to about budget_s. Value = frames/s the box would reach on
+        n_threads clips of clip_seconds (feed + flush), i.e. steps/s of the sample x frames-per-step of the benchmarked clip."""
+        w0, s0 = self.sample(n_threads, 0.5, first_id)
+        per_step = w0 / max(1, s0 / n_threads)                          # s per encoder step and thread (threads run side by side)
+        steps_budget = max(40.0, budget_s / per_step)
+        secs = min(clip_seconds, max(1.0, (steps_budget - 28) * 0.04))
+        wall, steps = self.sample(n_threads, secs, first_id + 100)
+        n_clip = int(16000 * clip_seconds)
+        clip_frames, clip_steps = FRAMES_PER_STREAM(n_clip), steps_of_clip(n_clip)
+        value = (steps / wall) * clip_frames / clip_steps
+        return {"value": value, "unit": "frames/s", "cores": n_threads, "kind": "reference",
+                "sample": "%d sessions x %.1f s of the same synthetic PCM, one native thread per session through aas_feed_pcm16 + aas_flush: %d encoder steps in %.1f s wall; scaled by encoder steps to %.0f s clips (%d frames per %d steps)" % (n_threads, secs, steps, wall, clip_seconds, clip_frames, clip_steps),
+                "encoder_steps_per_sec": steps / wall, "per_session_x_realtime": (steps / wall / n_threads) * clip_frames / clip_steps / 100.0,
+                "wall_s": wall + w0,
+                "note": "reference host sources compiled unmodified (oracle/_ref) over a CPU fp32 restatement of the ONNX graphs; ONNXRuntime itself is not in this image"}
+
+    def close(self):
+        self.m.close()
 
 
 def main():
@@ -132,9 +185,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sessions", type=int, default=64, help="sessions per GPU")
     ap.add_argument("--seconds", type=float, default=30.0)
-    ap.add_argument("--cpu-seconds", type=float, default=2.0, help="audio seconds per session in the CPU baseline sample")
+    ap.add_argument("--cpu-budget", type=float, default=None, help="wall seconds of one CPU sample (default: 20 s inside the b200 arm; 150 s / (steps + warmup) in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="bulk", choices=["bulk", "stream"], help="stream = BASELINE configs[3]: 40 ms chunks through the batched feed, per-chunk latency")
+    ap.add_argument("--no-extra", action="store_true", help="skip the b512 and stream blocks")
+    ap.add_argument("--mode", default="bulk", choices=["bulk", "stream"], help="stream = only BASELINE configs[3] (256 sessions x 40 ms chunks via aas_feed_pcm16)")
     ap.add_argument("--ticks", type=int, default=250)
     a = ap.parse_args()
 
@@ -142,6 +196,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workload = "%d concurrent sessions x %.0f s synthetic 16 kHz s16 PCM per GPU, feed whole clip + flush (BASELINE configs[%d]); random-init aprilv0-shaped LSTM-transducer (12 x LSTMP 1024/512 + FF 2048, vocab 500)" % (
+        a.sessions, a.seconds, 1 if world == 1 else 2)
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if a.impl == "reference":
@@ -149,22 +205,26 @@ def main():
             return
         path = ensure_model(0, None)
         nthr = max(1, min(ncores, 32))
+        arm = CpuArm(path)
+        budget = a.cpu_budget or max(4.0, 150.0 / max(1, a.steps + a.warmup))   # the whole run ends within a few minutes whatever K and W
         vals = []
         for i in range(a.warmup + a.steps):
-            fps, wall, frames = time_cpu_reference(path, a.cpu_seconds, nthr, first_id=1000 * i)
+            r = arm.measure(nthr, budget, a.seconds, first_id=1000 * i)
             if i >= a.warmup:
-                vals.append((fps, wall, frames))
-        fps = sum(v[2] for v in vals) / sum(v[1] for v in vals)
-        sample = "%d sessions x %.1f s of the same synthetic 16 kHz PCM, one thread per session, feed whole clip + flush" % (nthr, a.cpu_seconds)
+                vals.append(r)
+        arm.close()
+        fps = statistics.mean(v["value"] for v in vals)
+        cb = dict(vals[-1]); cb["value"] = fps
+        n_clip = int(16000 * a.seconds)
         print(json.dumps({
             "impl": "reference", "metric": "audio_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000.0 * sum(v[1] for v in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": 1000.0 * a.sessions * FRAMES_PER_STREAM(n_clip) / fps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "64 concurrent sessions x 30 s synthetic 16 kHz PCM (BASELINE configs[1]); CPU arm runs a bounded sample of it", "sample": sample},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthr, "kind": "reference", "sample": sample,
-                             "note": "reference host sources compiled unmodified over a CPU fp32 restatement of the ONNX graphs (ONNXRuntime itself is not in this image)"},
+            "config": {"workload": workload, "sessions_per_gpu": a.sessions, "seconds_per_session": a.seconds,
+                       "sample": cb["sample"], "ms_per_step_note": "time this box's %d host threads would need for one step of the workload (sessions x clip), from the sample" % nthr},
+            "cpu_baseline": cb,
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "x_realtime_per_stream": a.cpu_seconds / (sum(v[1] for v in vals) / len(vals)),
+            "x_realtime_per_stream": cb["per_session_x_realtime"],
         }))
         return
 
@@ -173,141 +233,167 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL_DEBUG=VERSION/INFO prints to stdout, which must carry exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    os.environ["APRIL_B200_DEVICE"] = str(local)
+    os.environ["APRIL_B200_DEVICE"] = str(local)       # one process per GPU: pin this process's models to its device
     import april_asr_b200 as A
+    import stream_driver as SD
     from april_asr_b200 import _ffi, dist_util
     from gen_pcm import gen_stream
 
     path = ensure_model(rank, dist)
     lib = A.Lib()
     m = A.Model(path, lib)
-    S, n = a.sessions, int(16000 * a.seconds)
-    pcms = [gen_stream(i, n) for i in dist_util.shard_stream_ids(rank, world, S)]
     handler = ctypes.cast(lib.c.aab_counting_handler, A.HANDLER)
-    counters = (ctypes.c_uint64 * 4)()
+    pk, pk_src = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
 
-    def make_sessions():
-        out = []
-        for _ in range(S):
-            cfg = A.AprilConfig(); cfg.handler = handler; cfg.userdata = ctypes.cast(counters, ctypes.c_void_p); cfg.flags = 0
-            h = lib.c.aas_create_session(m.handle, cfg)
-            assert h
-            out.append(h)
-        return out
+    def run_bulk(S, seconds, warmup, steps, stream_ids):
+        """warmup + steps passes of S fresh sessions x seconds; returns the per-config measurements (this rank's)."""
+        n = int(16000 * seconds)
+        pcms = [gen_stream(i, n) for i in stream_ids]
+        counters = (ctypes.c_uint64 * 4)()
+        hs_t = ctypes.c_void_p * S
+        ptrs = (ctypes.POINTER(ctypes.c_short) * S)(*[p.ctypes.data_as(ctypes.POINTER(ctypes.c_short)) for p in pcms])
+        cnts = (ctypes.c_size_t * S)(*[p.size for p in pcms])
 
-    hs_t = ctypes.c_void_p * S
-    ptrs = (ctypes.POINTER(ctypes.c_short) * S)(*[p.ctypes.data_as(ctypes.POINTER(ctypes.c_short)) for p in pcms])
-    cnts = (ctypes.c_size_t * S)(*[p.size for p in pcms])
-
-    def one_step():
-        ss = make_sessions()
-        arr = hs_t(*ss)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rc = lib.c.aab_feed_pcm16_batch(arr, ptrs, cnts, S)
-        rc |= lib.c.aab_flush_batch(arr, S)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        assert rc == 0
-        for h in ss:
-            lib.c.aas_free(h)
-        return dt
-
-    if a.mode == "stream":
-        # BASELINE configs[3]: S sessions fed 40 ms (640-sample) chunks; latency = time inside one batched feed call
-        # (handlers run before it returns), measured on the host around the C-ABI call.
-        ss = make_sessions()
-        arr = hs_t(*ss)
-        chunk = 640
-        lat = []
-        for k in range(a.ticks + 20):
-            off = (k * chunk) % (n - chunk)
-            p2 = (ctypes.POINTER(ctypes.c_short) * S)(*[ctypes.cast(p.ctypes.data + 2 * off, ctypes.POINTER(ctypes.c_short)) for p in pcms])
-            c2 = (ctypes.c_size_t * S)(*([chunk] * S))
+        def one_step():
+            ss = []
+            for _ in range(S):
+                cfg = A.AprilConfig(); cfg.handler = handler; cfg.userdata = ctypes.cast(counters, ctypes.c_void_p); cfg.flags = 0
+                h = lib.c.aas_create_session(m.handle, cfg)
+                assert h
+                ss.append(h)
+            arr = hs_t(*ss)
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            rc = lib.c.aab_feed_pcm16_batch(arr, p2, c2, S)
+            rc = lib.c.aab_feed_pcm16_batch(arr, ptrs, cnts, S)
+            rc |= lib.c.aab_flush_batch(arr, S)
+            torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             assert rc == 0
-            if k >= 20:
-                lat.append(dt * 1e3)
-        lat.sort()
-        p50, p99 = lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))]
+            for h in ss:
+                lib.c.aas_free(h)
+            return dt
+        for _ in range(warmup):
+            one_step()
+        st = _ffi.AprilB200Stats()
+        lib.c.aab_set_timing(m.handle, 1)
+        lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
+        for i in range(4):
+            counters[i] = 0
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if rank == 0 else None
+        walls = [one_step() for _ in range(steps)]
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
+        lib.c.aab_set_timing(m.handle, 0)
+        return {"S": S, "n": n, "walls": walls, "st": st, "clocks": clocks, "counters": [int(x) for x in counters]}
+
+    def roofline_of(r, steps):
+        st = r["st"]
+        sess_steps = st.encoder_steps                                       # session-steps over the timed steps
+        scan_s, lgemm_s = st.lstm_scan_ms / 1e3, st.lstm_gemm_ms / 1e3
+        scan_tf = sess_steps * FLOP_PER_STEP_RECURRENT / max(1e-9, scan_s) / 1e12
+        lstm_tf = sess_steps * FLOP_PER_STEP_LSTM_GEMM / max(1e-9, scan_s + lgemm_s) / 1e12
+        gemm_tf = st.gemm_flops / max(1e-9, st.gemm_ms / 1e3) / 1e12
+        whole_tf = sess_steps * FLOP_PER_STEP_ENCODER / max(1e-9, st.compute_ms / 1e3) / 1e12
+        layer_steps = max(1.0, (sess_steps / r["S"]) * 12)
+        tr = ncu_traffic("lstm_scan4_kernel")
+        return {"bound": "tensor", "kernel": "scan4::lstm_scan4_kernel (recurrent W_hh / W_hr part of one LSTM layer: all steps of a pass, up to 512 sessions per launch; %.0f %% of the step)" % (100.0 * st.lstm_scan_ms / max(1e-9, st.compute_ms)),
+                "achieved": scan_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": scan_tf / peak_tf,
+                "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": tr["bytes"] if tr else None,
+                "traffic_note": ("dram bytes read + written by one launch, from the committed ncu page %s" % tr["file"]) if tr else "no ncu --set full capture of this kernel committed under profiles/ yet",
+                "algorithmic_note": "FLOPs per launch = steps x sessions x 2 x (4H x D + D x H) (the reference's W_hh and W_hr products, counted once; the kernel issues 3 fp16 products per algorithmic product over W_eff = W_hh W_hr); duration = CUDA events on the engine stream around every launch of the timed steps",
+                "us_per_layer_step": 1e6 * scan_s / layer_steps,
+                "lstm_gemm_subset": {"what": "W_ih + W_hh + W_hr of all layers (113.25 MFLOP per session-step): the scan launches plus the W_ih and W_hr GEMM launches",
+                                     "achieved": lstm_tf, "frac": lstm_tf / peak_tf, "ms_per_step": 1e3 * (scan_s + lgemm_s) / steps},
+                "gemm": {"kernel": "tc::gemm_tc_kernel<3,*,2> time-batched projections (W_ih, W_hr out, FF1, FF2, conv3, conv-out, enc_proj), CTA pairs 256x256x64",
+                         "achieved": gemm_tf, "frac": gemm_tf / peak_tf, "ms_per_step": st.gemm_ms / steps, "note": "3 MMAs per algorithmic product: the tensor pipe does 3x this figure"},
+                "ms_per_step_by_class": {"lstm_scan": st.lstm_scan_ms / steps, "gemm": st.gemm_ms / steps, "of_which_lstm_gemm": st.lstm_gemm_ms / steps,
+                                         "joiner_greedy": st.greedy_ms / steps, "fbank": st.frontend_ms / steps},
+                "whole_pass": {"achieved": whole_tf, "frac": whole_tf / peak_tf, "what": "168.39 MFLOP of encoder per session-step over the whole device-resident pass"},
+                "precision": "fp16x3 split (3 tensor-core products per algorithmic product, fp32 accumulation in TMEM); algorithmic FLOPs counted once"}
+
+    def stream_block(S, ticks):
+        n = 16000 * 12
+        pcms = [gen_stream(10_000 + i, n) for i in range(S)]
+        st = _ffi.AprilB200Stats()
+        lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
+        lat, cnt = SD.stream(lib, m.handle, pcms, 640, 20, ticks, 0)
+        lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
+        per_tick = np.sort(lat.max(axis=1))                              # a tick is done when its slowest stream has its callbacks
+        flat = np.sort(lat.reshape(-1))
+        q = lambda v, p: float(v[min(len(v) - 1, int(len(v) * p))])
+        return {"workload": "%d synchronous sessions, one native thread each, 40 ms (640-sample) chunks through plain aas_feed_pcm16, all streams' chunks arriving together (BASELINE configs[3])" % S,
+                "sessions": S, "ticks": ticks, "latency_ms": {"p50": q(flat, 0.5), "p99": q(flat, 0.99), "max": float(flat[-1])},
+                "latency_note": "per chunk and stream: aas_feed_pcm16 returned - entered; a synchronous session's handler runs before the call returns",
+                "tick_ms": {"p50": q(per_tick, 0.5), "p99": q(per_tick, 0.99)},
+                "x_realtime_per_stream": 40.0 / q(per_tick, 0.5), "frames_per_sec": S * 4 / (float(per_tick.mean()) / 1e3),
+                "device_passes": int(st.passes), "mean_sessions_per_pass": st.pass_sessions / max(1, st.passes), "callbacks": cnt}
+
+    if a.mode == "stream":
+        sb = stream_block(a.sessions if a.sessions != 64 else 256, a.ticks)
         if rank == 0:
-            print(json.dumps({"metric": "chunk_latency_ms", "mode": "stream", "sessions": S, "chunk_ms": 40, "ticks": a.ticks, "p50_ms": p50, "p99_ms": p99,
-                              "mean_ms": sum(lat) / len(lat), "frames_per_sec": S * 4 / (sum(lat) / len(lat) / 1e3), "x_realtime_per_stream": 40.0 / (sum(lat) / len(lat)),
-                              "config": {"workload": "%d sessions streaming 40 ms chunks through aab_feed_pcm16_batch (BASELINE configs[3]), 1 GPU" % S}}))
-        for h in ss:
-            lib.c.aas_free(h)
+            print(json.dumps({"metric": "chunk_latency_ms", "value": sb["latency_ms"]["p50"], "unit": "ms", "n_gpus": world, "steps": a.ticks, "warmup": 20, "higher_is_better": False,
+                              "ms_per_step": sb["tick_ms"]["p50"], "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": sb["workload"]}, "stream": sb}))
         m.close()
         return
-    for _ in range(a.warmup):
-        one_step()
-    st = _ffi.AprilB200Stats()
-    lib.c.aab_set_timing(m.handle, 1)
-    lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
-    walls = [one_step() for _ in range(a.steps)]
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    clocks = sampler.stop() if sampler else None
-    lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
-    lib.c.aab_set_timing(m.handle, 0)
 
-    (wall_s, compute_s), (frames_step,) = dist_util.combine(dist, "cuda", [sum(walls), st.compute_ms / 1e3], [S * FRAMES_PER_STREAM(n)])
+    r = run_bulk(a.sessions, a.seconds, a.warmup, a.steps, dist_util.shard_stream_ids(rank, world, a.sessions))
+    st = r["st"]
+    (wall_s, compute_s), (frames_step,) = dist_util.combine(dist, "cuda", [sum(r["walls"]), st.compute_ms / 1e3], [a.sessions * FRAMES_PER_STREAM(r["n"])])
     frames_total = frames_step * a.steps
-
+    out = None
     if rank == 0:
-        pk, pk_src = peaks()
-        steps_per_pass = st.encoder_steps / a.steps
-        gemm_tflops = st.gemm_flops / (st.gemm_ms / 1e3) / 1e12 if st.gemm_ms > 0 else None
-        peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        scan_tflops = (st.encoder_steps * 2.0 * 31_457_280) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e12
         out = {
             "metric": "audio_frames_per_sec", "value": frames_total / compute_s, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000.0 * compute_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d concurrent sessions x %.0f s synthetic 16 kHz s16 PCM per GPU, feed whole clip + flush (BASELINE configs[%d]); random-init aprilv0-shaped LSTM-transducer (12 x LSTMP 1024/512 + FF 2048, vocab 500)" % (S, a.seconds, 1 if world == 1 else 2),
-                       "sessions_per_gpu": S, "seconds_per_session": a.seconds, "parallelism": "sessions sharded, %d per GPU, no collective on the data path" % S,
+            "dtype": "f32 (fp16x3-split tensor-core products, fp32 accumulate and fp32 everywhere else)", "data": "synthetic",
+            "config": {"workload": workload, "sessions_per_gpu": a.sessions, "seconds_per_session": a.seconds,
+                       "parallelism": "sessions sharded, %d per GPU, no collective on the data path" % a.sessions,
                        "l2": "working set (337 MB fp32 weights + GBs of activations per pass) exceeds the 126 MB L2; no explicit flush",
-                       "timing": "value: CUDA events on the engine stream around the device-resident part of each pass (after the PCM upload), max over ranks; e2e: wall clock around the C-ABI calls with host buffers"},
+                       "timing": "value: device-resident part of each pass (CUDA events on the engine stream, after the PCM upload), max over ranks; e2e: wall clock around the C-ABI calls with host buffers (staging, H2D, compute, D2H, callbacks)"},
             "x_realtime_per_stream": a.seconds / (compute_s / a.steps),
             "e2e": {"value": frames_total / wall_s, "unit": "frames/s", "ms_per_step": 1000.0 * wall_s / a.steps,
                     "h2d_bytes_per_step": st.h2d_bytes / a.steps, "d2h_bytes_per_step": st.d2h_bytes / a.steps,
                     "x_realtime_per_stream": a.seconds / (wall_s / a.steps)},
             "gpu_launches": int(st.kernel_launches),
-            "clocks": clocks,
-            # dominant kernel of the step: the persistent recurrent scan (one launch = one LSTM layer over all steps of a pass).
-            # algorithmic FLOPs = the reference's W_hh (4H x D) and W_hr (D x H) products per session-step, counted once.
-            "roofline": {"bound": "tensor", "kernel": "scan3::lstm_scan3_kernel (recurrent W_hh / W_hr part of one LSTM layer, all steps of a pass; %.0f %% of the step)" % (100.0 * st.lstm_scan_ms / max(1e-9, st.compute_ms)),
-                         "achieved": scan_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": scan_tflops / peak_tf,
-                         "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
-                         "traffic": 1173.2e6, "traffic_note": "dram bytes read + written by one launch (748 steps x 64 sessions), ncu --set full, profiles/r01b_ncu_scan3.raw.csv; algorithmic bytes of that launch: 784e6 (gate pre-activations G, fp32) + 196e6 (m out, fp16 hi/lo) + 16.8e6 (W_eff slice set) = 997e6",
-                         "why_far_from_peak": "latency-bound dependent chain: %d sequential layer-steps per pass, each a grid-wide exchange of m(t) through L2 (TMA landing ~0.7 us + MMA + TMEM drain + pair exchange + cell + release ~1 us + acquire ~1.5 us); N = 64 sessions per MMA and a measured >= 84 clk issue cost per tcgen05.mma whatever its N (profiles/r01b_summary.md)" % int(12 * steps_per_pass / S),
-                         "us_per_layer_step": 1e3 * st.lstm_scan_ms / max(1.0, (st.encoder_steps / S) * 12),
-                         "hbm_view": {"achieved_GBps": (st.encoder_steps * 12 * (4 * 1024 * 4 + 2 * 1024 * 2)) / max(1e-9, st.lstm_scan_ms / 1e3) / 1e9, "peak_GBps": pk.get("hbm_gbs"), "note": "algorithmic bytes: fp32 gate rows in, fp16 (hi, lo) m rows out, per session-step and layer"},
-                         "precision": "fp16x3 split (3-4 tensor-core products per algorithmic product; callbacks identical to the fp32 reference on 23 of 24 checked 30 s streams); algorithmic FLOPs counted once",
-                         "gemm": {"kernel": "tc::gemm_tc_kernel<3,*,2> time-batched projections (W_ih, W_hr out, FF1, FF2, conv3, conv-out, enc_proj), CTA pairs 256x256x64",
-                                  "achieved": gemm_tflops, "frac": (gemm_tflops / peak_tf) if gemm_tflops else None, "ms_per_step": st.gemm_ms / a.steps,
-                                  "note": "3 MMAs per algorithmic product: the tensor pipe does 3x this figure"},
-                         "gemm_ms_per_step": st.gemm_ms / a.steps, "greedy_ms_per_step": st.greedy_ms / a.steps, "lstm_scan_ms_per_step": st.lstm_scan_ms / a.steps,
-                         "whole_pass_tflops": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12,
-                         "whole_pass_frac": steps_per_pass * FLOP_PER_STEP_ENCODER / (st.compute_ms / a.steps / 1e3) / 1e12 / peak_tf},
-            "results": {"partial_callbacks": int(counters[0]), "final_callbacks": int(counters[1]), "silence_callbacks": int(counters[2]), "final_tokens": int(counters[3]),
-                        "encoder_steps_per_pass": steps_per_pass, "joiner_passes_per_pass": st.joiner_passes / a.steps},
+            "clocks": r["clocks"],
+            "comm": {"backend": "nccl" if world > 1 else None, "nranks": world, "use": "start/stop barrier and max-over-ranks of the timings only"},
+            "roofline": roofline_of(r, a.steps),
+            "results": {"partial_callbacks": r["counters"][0], "final_callbacks": r["counters"][1], "silence_callbacks": r["counters"][2], "final_tokens": r["counters"][3],
+                        "encoder_steps_per_pass": st.encoder_steps / a.steps, "joiner_passes_per_pass": st.joiner_passes / a.steps},
         }
-        if not a.no_cpu_baseline and world == 1:
+    if world == 1 and not a.no_extra:
+        # north_star's operating point on one GPU, and configs[3], in the same process (weights already resident)
+        if a.sessions != 512:
+            rb = run_bulk(512, a.seconds, 1, 2, range(512))
+            sb_st, steps_b = rb["st"], 2
+            comp = sb_st.compute_ms / 1e3
+            fr = 512 * FRAMES_PER_STREAM(rb["n"]) * steps_b
+            out["b512"] = {"workload": "512 concurrent sessions x %.0f s on this one GPU (north_star operating point; configs[2] puts 64 on each of 8 GPUs instead)" % a.seconds,
+                           "value": fr / comp, "unit": "frames/s", "steps": steps_b, "warmup": 1, "ms_per_step": 1e3 * comp / steps_b, "x_realtime_per_stream": a.seconds / (comp / steps_b),
+                           "e2e": {"value": fr / sum(rb["walls"]), "unit": "frames/s", "ms_per_step": 1e3 * sum(rb["walls"]) / steps_b,
+                                   "h2d_bytes_per_step": sb_st.h2d_bytes / steps_b, "d2h_bytes_per_step": sb_st.d2h_bytes / steps_b},
+                           "clocks": rb["clocks"], "roofline": roofline_of(rb, steps_b), "final_tokens": rb["counters"][3]}
+        out["stream"] = stream_block(256, a.ticks)
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1 and os.path.exists(ORACLE_SO):
+            arm = CpuArm(path)
             nthr = max(1, min(ncores, 32))
-            fps, wall, frames = time_cpu_reference(path, a.cpu_seconds, nthr, first_id=5000)
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": nthr, "kind": "reference", "per_session_frames_per_sec": fps / nthr, "per_session_x_realtime": fps / nthr / 100.0,
-                                   "sample": "%d sessions x %.1f s of the same synthetic PCM, one thread per session (reference uses 1 ORT thread per session), feed + flush; %.1f s wall" % (nthr, a.cpu_seconds, wall),
-                                   "note": "reference host sources compiled unmodified + CPU fp32 restatement of the ONNX graphs (ONNXRuntime unavailable in this image)"}
+            cb = arm.measure(nthr, a.cpu_budget or 20.0, a.seconds, first_id=5000)
+            one = arm.measure(1, (a.cpu_budget or 20.0) / 2, 10.0, first_id=7000)           # configs[0]: one session, one core, 10 s clip
+            cb["single_session"] = {"value": one["value"], "unit": "frames/s", "x_realtime": one["per_session_x_realtime"], "sample": one["sample"],
+                                    "workload": "BASELINE configs[0]: 1 session, 10 s clip, 1 core"}
+            arm.close()
+            out["cpu_baseline"] = cb
         print(json.dumps(out))
     m.close()
     if dist is not None:

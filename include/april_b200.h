@@ -62,6 +62,9 @@ typedef struct AprilB200Stats {
     double   greedy_ms;         /* ... of which the joiner + greedy search kernel */
     uint64_t passes;            /* batched device passes run */
     uint64_t pass_sessions;     /* sessions summed over those passes (pass_sessions / passes = mean batch) */
+    double   lstm_gemm_ms;      /* part of gemm_ms spent in the W_ih and W_hr (layer output) GEMMs */
+    double   lstm_gemm_flops;   /* their algorithmic FLOPs */
+    double   frontend_ms;       /* fbank kernel + feature-row carry */
 } AprilB200Stats;
 
 /* Cumulative statistics of a model's engine; reset != 0 zeroes them after reading. lstm_scan_ms / gemm_ms /

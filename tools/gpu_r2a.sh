@@ -13,12 +13,12 @@ timeout 600 python tools/scan_check.py --model full --sessions 130 --seconds 3 -
 timeout 600 python tools/scan_check.py --model full --sessions 130 --seconds 3 --a "APRIL_B200_SCAN_CS=4 APRIL_B200_SCAN_MMAW=1" --b "APRIL_B200_SCAN_MMAW=2" > $O/check_cs4m1_cs2m2.log 2>&1
 tail -n 3 $O/check_*.log
 
-run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline $BARGS 2>&1 | python -c "
+run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra $BARGS 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('scan trace') or l.startswith('  '): print(l.rstrip())
     elif l.startswith('{'):
-        d=json.loads(l); r=d['roofline']; print('$tag', 'ms/step', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'scan_ms', round(r['lstm_scan_ms_per_step'],2), 'us/layer-step', round(r['us_per_layer_step'],3), 'gemm_ms', round(r['gemm_ms_per_step'],2), 'greedy_ms', round(r.get('greedy_ms_per_step',0),2), 'tokens', d['results']['final_tokens'])
+        d=json.loads(l); r=d['roofline']; c=r['ms_per_step_by_class']; print('$tag', 'ms/step', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'scan_ms', round(c['lstm_scan'],2), 'us/layer-step', round(r['us_per_layer_step'],3), 'gemm_ms', round(c['gemm'],2), 'lstm_gemm_ms', round(c['of_which_lstm_gemm'],2), 'greedy_ms', round(c['joiner_greedy'],2), 'fbank_ms', round(c['fbank'],2), 'tokens', d['results']['final_tokens'])
     elif 'timeout' in l or 'rror' in l or 'libapril' in l: print(l.rstrip())
 " | tail -6; }
 {
