@@ -239,7 +239,7 @@ def main():
     import april_asr_b200 as A
     import stream_driver as SD
     from april_asr_b200 import _ffi, dist_util
-    from gen_pcm import gen_stream
+    from gen_pcm import gen_stream, gen_streams
 
     path = ensure_model(rank, dist)
     lib = A.Lib()
@@ -251,7 +251,7 @@ def main():
     def run_bulk(S, seconds, warmup, steps, stream_ids):
         """warmup + steps passes of S fresh sessions x seconds; returns the per-config measurements (this rank's)."""
         n = int(16000 * seconds)
-        pcms = [gen_stream(i, n) for i in stream_ids]
+        pcms = gen_streams(stream_ids, n)
         counters = (ctypes.c_uint64 * 4)()
         hs_t = ctypes.c_void_p * S
         ptrs = (ctypes.POINTER(ctypes.c_short) * S)(*[p.ctypes.data_as(ctypes.POINTER(ctypes.c_short)) for p in pcms])
@@ -323,7 +323,7 @@ def main():
 
     def stream_block(S, ticks):
         n = 16000 * 12
-        pcms = [gen_stream(10_000 + i, n) for i in range(S)]
+        pcms = gen_streams(range(10_000, 10_000 + S), n)
         st = _ffi.AprilB200Stats()
         lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
         lat, cnt = SD.stream(lib, m.handle, pcms, 640, 20, ticks, 0)

@@ -57,6 +57,22 @@ def _onepole(x, a):
         return y
 
 
+def _gen_job(args):
+    return gen_stream(*args)
+
+
+def gen_streams(stream_ids, n_samples, workers=None):
+    """Many streams: worker processes (spawned, so it is safe after CUDA has been initialised) when the job is big."""
+    ids = list(stream_ids)
+    if len(ids) * n_samples < 64 * 480000 + 1:
+        return [gen_stream(i, n_samples) for i in ids]
+    import multiprocessing as mp
+    import os
+    workers = workers or max(2, min(16, (os.cpu_count() or 4)))
+    with mp.get_context("spawn").Pool(workers) as pool:
+        return pool.map(_gen_job, [(i, n_samples) for i in ids], chunksize=8)
+
+
 def gen_batch(n_streams, n_samples, first_id=0):
     return np.stack([gen_stream(first_id + i, n_samples) for i in range(n_streams)])
 
