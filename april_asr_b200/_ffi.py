@@ -50,7 +50,7 @@ REFERENCE_SYMBOLS = [
 ]
 B200_SYMBOLS = [
     "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_session_device", "aab_get_stats",
-    "aab_set_tap", "aab_engine_version", "aab_debug_fbank", "aab_set_timing", "aab_counting_handler", "aab_debug_gemm", "aab_debug_replay", "aab_debug_plan",
+    "aab_set_tap", "aab_engine_version", "aab_debug_fbank", "aab_set_timing", "aab_counting_handler", "aab_debug_gemm", "aab_debug_replay", "aab_debug_plan", "aab_debug_model_digest",
 ]
 
 
@@ -94,5 +94,6 @@ class Lib:
             c.aab_debug_plan.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
             c.aab_debug_plan.restype = ctypes.c_int
             c.aab_set_timing.argtypes, c.aab_set_timing.restype = [vp, ctypes.c_int], None
+            c.aab_debug_model_digest.argtypes, c.aab_debug_model_digest.restype = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)], ctypes.c_int
             c.aab_get_stats.argtypes, c.aab_get_stats.restype = [vp, ctypes.POINTER(AprilB200Stats), ctypes.c_int], ctypes.c_int
         c.aam_api_init(1)

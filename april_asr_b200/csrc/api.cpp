@@ -517,6 +517,15 @@ APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_rec
     return r;
 }
 
+APRIL_EXPORT int aab_debug_model_digest(const char* model_path, uint64_t* out16) {
+    if (!model_path || !out16) return -1;
+    LoadedModel lm;
+    std::string err;
+    if (!load_april_file(model_path, lm, err)) { LOG_INFO("aab_debug_model_digest: %s", err.c_str()); return -1; }
+    model_digest(lm, out16);
+    return 0;
+}
+
 APRIL_EXPORT int aab_debug_plan(const char* model_path, int n_calls, const size_t* counts, const int* flush, int* out_steps, int* out_frames) {
     if (!model_path || n_calls < 0 || (n_calls && (!counts || !flush || !out_steps || !out_frames))) return -1;
     LoadedModel lm;

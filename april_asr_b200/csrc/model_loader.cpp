@@ -123,8 +123,8 @@ bool parse_tensor(Pb c, OTensor& t) {
         else if (f == 5) { if (wt == 0) t.i.push_back((int64_t)(int32_t)v); else while (sub.p < sub.end && sub.ok) t.i.push_back((int64_t)(int32_t)sub.varint()); }
     }
     if (!c.ok) return false;
-    int64_t n = t.numel();
-    if (n < 0) return false;
+    int64_t n = 1;
+    for (auto d : t.dims) { if (d < 0 || d > ((int64_t)1 << 31)) return false; n *= d; if (n > ((int64_t)1 << 40)) return false; }   // no negative / overflowing shapes
     if (has_raw) {
         if (t.dtype == ONNX_FLOAT) { if ((int64_t)raw_len != n * 4) return false; t.raw = raw; }
         else if (t.dtype == ONNX_INT64) { if ((int64_t)raw_len != n * 8) return false; t.i.resize((size_t)n); std::memcpy(t.i.data(), raw, raw_len); }
@@ -233,9 +233,11 @@ struct GraphView {
 // Collect Linear layers in graph order: Gemm(x, W[out,in] (transB=1), b) or MatMul(x, Wt[in,out]) (+ Add(bias)).
 bool collect_linears(const GraphView& gv, const std::string& h_input, std::vector<Linear>& out, std::string& err) {
     for (auto& n : gv.g.nodes) {
+        if ((n.op == "Gemm" || n.op == "MatMul") && (n.in.size() < 2 || n.out.empty())) { err = "ONNX: " + n.op + " node with missing inputs / outputs"; return false; }
         if (n.op == "Gemm") {
             const OTensor* w = n.in.size() > 1 ? gv.constant(n.in[1]) : nullptr;
             if (!w || w->dims.size() != 2 || w->dtype != ONNX_FLOAT) continue;
+            if (w->dims[0] <= 0 || w->dims[1] <= 0 || w->dims[0] > (1 << 20) || w->dims[1] > (1 << 20)) { err = "ONNX: Gemm weight dims out of range"; return false; }
             auto ta = n.ints.find("transA"), tb = n.ints.find("transB");
             bool transA = ta != n.ints.end() && !ta->second.empty() && ta->second[0];
             bool transB = tb != n.ints.end() && !tb->second.empty() && tb->second[0];
@@ -251,6 +253,7 @@ bool collect_linears(const GraphView& gv, const std::string& h_input, std::vecto
         } else if (n.op == "MatMul") {
             const OTensor* w = n.in.size() > 1 ? gv.constant(n.in[1]) : nullptr;
             if (!w || w->dims.size() != 2 || w->dtype != ONNX_FLOAT) continue;
+            if (w->dims[0] <= 0 || w->dims[1] <= 0 || w->dims[0] > (1 << 20) || w->dims[1] > (1 << 20)) { err = "ONNX: MatMul weight dims out of range"; return false; }
             Linear l; l.in = (int)w->dims[0]; l.out = (int)w->dims[1];
             l.w = w->copy_f_transposed(l.in, l.out);
             l.from_h = !h_input.empty() && gv.derives_from(n.in[0], h_input);
@@ -293,8 +296,10 @@ bool extract_encoder(const OGraph& g, ModelWeights& W, std::string& err) {
     if (!xd || !hd || !cd || xd->size() != 3 || hd->size() != 3 || cd->size() != 3) FAIL("encoder: inputs x,h,c with static 3-D shapes required");
     ModelDims& d = W.d;
     if ((*xd)[0] != 1 || (*hd)[1] != 1 || (*cd)[1] != 1) FAIL("encoder: graphs must be exported with batch 1 (params.c:71)");
+    for (auto* v : { xd, hd, cd }) for (auto e : *v) if (e <= 0 || e > (1 << 20)) FAIL("encoder: input dims must be positive static sizes");
     d.SEG = (int)(*xd)[1]; d.MEL = (int)(*xd)[2]; d.L = (int)(*hd)[0]; d.D = (int)(*hd)[2]; d.H = (int)(*cd)[2];
     if ((*cd)[0] != d.L) FAIL("encoder: h/c layer count mismatch");
+    if (d.L > 64 || d.SEG < 7) FAIL("encoder: layer count / segment size out of range");
 
     // convolutions, in order
     std::vector<const ONode*> convs;
@@ -304,9 +309,11 @@ bool extract_encoder(const OGraph& g, ModelWeights& W, std::string& err) {
     std::vector<float>* cw[3] = { &W.conv1_w, &W.conv2_w, &W.conv3_w }; std::vector<float>* cb[3] = { &W.conv1_b, &W.conv2_b, &W.conv3_b };
     int cout[3], cin[3];
     for (int k = 0; k < 3; k++) {
+        if (convs[k]->in.size() < 2 || convs[k]->out.empty()) FAIL("encoder: Conv node with missing inputs / outputs");
         const OTensor* w = gv.constant(convs[k]->in[1]);
         const OTensor* b = convs[k]->in.size() > 2 ? gv.constant(convs[k]->in[2]) : nullptr;
         if (!w || w->dims.size() != 4 || w->dims[2] != 3 || w->dims[3] != 3 || !b) FAIL("encoder: Conv must be 3x3 with constant weight and bias");
+        if (w->dtype != ONNX_FLOAT || b->dtype != ONNX_FLOAT || w->dims[0] <= 0 || w->dims[1] <= 0 || w->dims[0] > 4096 || w->dims[1] > 4096) FAIL("encoder: Conv weights must be float with sane channel counts");
         auto st = convs[k]->ints.find("strides"); int s = (st != convs[k]->ints.end() && !st->second.empty()) ? (int)st->second[0] : 1;
         auto pd = convs[k]->ints.find("pads"); if (pd != convs[k]->ints.end()) for (auto p : pd->second) if (p != 0) FAIL("encoder: Conv padding unsupported");
         auto gr = convs[k]->ints.find("group"); if (gr != convs[k]->ints.end() && !gr->second.empty() && gr->second[0] != 1) FAIL("encoder: grouped Conv unsupported");
@@ -318,7 +325,7 @@ bool extract_encoder(const OGraph& g, ModelWeights& W, std::string& err) {
     if (cin[0] != 1 || cin[1] != cout[0] || cin[2] != cout[1]) FAIL("encoder: Conv channel chain mismatch");
     d.C1 = cout[0]; d.C2 = cout[1]; d.C3 = cout[2];
     int t1 = d.SEG - 2, f1 = d.MEL - 2, t2 = (t1 - 3) / 2 + 1, f2 = (f1 - 3) / 2 + 1, t3 = (t2 - 3) / 2 + 1, f3 = (f2 - 3) / 2 + 1;
-    if (t3 != 1) FAIL("encoder: segment size must reduce to exactly one output frame");
+    if (t3 != 1 || f3 <= 0) FAIL("encoder: segment size must reduce to exactly one output frame (and at least one frequency bin)");
     d.F3 = f3;
 
     std::vector<Linear> lin;
@@ -374,14 +381,19 @@ bool extract_decoder(const OGraph& g, ModelWeights& W, std::string& err) {
     const ONode* gather = nullptr; const ONode* conv = nullptr;
     for (auto& n : g.nodes) { if (n.op == "Gather" && !gather) gather = &n; if (n.op == "Conv" && !conv) conv = &n; }
     if (!gather) FAIL("decoder: no embedding Gather");
+    if (gather->in.size() < 2) FAIL("decoder: Gather node with missing inputs");
     const OTensor* emb = gv.constant(gather->in[0]);
     if (!emb || emb->dims.size() != 2) FAIL("decoder: embedding table must be a 2-D constant");
     if (emb->dtype != ONNX_FLOAT) FAIL("decoder: embedding must be float");
+    if (emb->dims[0] <= 0 || emb->dims[1] <= 0 || emb->dims[0] > (1 << 20) || emb->dims[1] > (1 << 16)) FAIL("decoder: embedding dims out of range");
+    if (d.CTX <= 0 || d.CTX > 16) FAIL("decoder: context size out of range");
     d.V = (int)emb->dims[0]; d.E = (int)emb->dims[1]; W.emb = emb->copy_f();
     if (d.CTX > 1) {
         if (!conv) FAIL("decoder: context_size > 1 needs the Conv1d");
+        if (conv->in.size() < 2) FAIL("decoder: Conv node with missing inputs");
         const OTensor* w = gv.constant(conv->in[1]);
         auto gr = conv->ints.find("group"); int group = (gr != conv->ints.end() && !gr->second.empty()) ? (int)gr->second[0] : 1;
+        if (w && w->dtype != ONNX_FLOAT) FAIL("decoder: Conv weight must be float");
         if (!w || w->dims.size() != 3 || w->dims[0] != d.E || w->dims[1] != 1 || w->dims[2] != d.CTX || group != d.E || conv->in.size() > 2)
             FAIL("decoder: only the depthwise, bias-free Conv1d(kernel = context_size) is supported");
         W.dec_conv_w = w->copy_f();
@@ -425,6 +437,7 @@ bool read_params(Bytes& b, Params& p, std::string& err) {
               p.frame_shift_ms <= p.frame_length_ms && p.frame_length_ms > 0 && p.frame_length_ms <= 5000 && p.mel_low > 0 &&
               p.mel_low < p.sample_rate && (p.mel_high == 0 || p.mel_high > p.mel_low);
     if (!ok) FAIL("params: value out of the accepted range (src/params.c:71-82)");
+    if (p.frame_shift_ms * p.sample_rate / 1000 <= 0 || p.frame_length_ms * p.sample_rate / 1000 < 2) FAIL("params: frame shift / length of less than one sample at this sample rate");
     p.tokens.resize((size_t)p.token_count);
     for (int i = 0; i < p.token_count; i++) {
         int32_t n = b.rd<int32_t>();
@@ -487,6 +500,21 @@ bool load_april_file(const std::string& path, LoadedModel& out, std::string& err
     if (d.V != out.params.token_count) FAIL("logits dim does not match token_count (april_model.c:102)");
     if (d.CTX != 2) FAIL("only context_size 2 is supported (the reference's greedy search hard-codes it: april_session.c:322,326)");
     return true;
+}
+
+void model_digest(const LoadedModel& m, uint64_t out[16]) {
+    const ModelDims& d = m.w.d;
+    const int dims[15] = { d.L, d.D, d.H, d.F, d.J, d.E, d.V, d.CTX, d.MEL, d.SEG, d.STEP, d.C1, d.C2, d.C3, d.F3 };
+    for (int i = 0; i < 15; i++) out[i] = (uint64_t)dims[i];
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    auto vec = [&](const std::vector<float>& v) { const uint64_t n = v.size(); mix(&n, 8); if (n) mix(v.data(), n * 4); };
+    const ModelWeights& w = m.w;
+    for (auto* v : { &w.conv1_w, &w.conv1_b, &w.conv2_w, &w.conv2_b, &w.conv3_w, &w.conv3_b, &w.out_w, &w.out_b }) vec(*v);
+    mix(&w.out_norm_eps, 4);
+    for (auto& l : w.layers) { for (auto* v : { &l.w_ih, &l.b_ih, &l.w_hh, &l.b_hh, &l.w_hr, &l.ff1_w, &l.ff1_b, &l.ff2_w, &l.ff2_b }) vec(*v); mix(&l.norm_eps, 4); }
+    for (auto* v : { &w.enc_proj_w, &w.enc_proj_b, &w.emb, &w.dec_conv_w, &w.dec_proj_w, &w.dec_proj_b, &w.join_w, &w.join_b }) vec(*v);
+    out[15] = h;
 }
 
 }  // namespace april

@@ -58,4 +58,9 @@ struct LoadedModel {
 // Returns false and fills `err` on any malformed / unsupported input.
 bool load_april_file(const std::string& path, LoadedModel& out, std::string& err);
 
+// Test hook (CPU only): order-independent-of-graph-structure fingerprint of what the loader extracted: out[0..14] = the model
+// dims (L, D, H, F, J, E, V, CTX, MEL, SEG, STEP, C1, C2, C3, F3), out[15] = FNV-1a over every weight array in canonical order
+// (bit patterns) and the norm eps values. Two files holding the same network in differently structured graphs give equal digests.
+void model_digest(const LoadedModel& m, uint64_t out[16]);
+
 }  // namespace april

@@ -105,6 +105,11 @@ APRIL_EXPORT int aab_debug_replay(const char* model_path, int n_steps, int n_rec
  * the frames computed per call. Returns 0, or -1 on a bad model file. */
 APRIL_EXPORT int aab_debug_plan(const char* model_path, int n_calls, const size_t* counts, const int* flush, int* out_steps, int* out_frames);
 
+/* Test hook, CPU only: loads a .april file with the product's loader (container, params, topology-driven weight extraction from the
+ * three ONNX graphs: model_loader.cpp, replacing src/file/model_file.c:58-185 + ONNXRuntime's model loading) and writes a
+ * fingerprint: out16[0..14] = the dims it found, out16[15] = a hash over every extracted weight array in canonical order.
+ * Returns 0, or -1 when the loader rejects the file (nothing is written, nothing crashes). */
+APRIL_EXPORT int aab_debug_model_digest(const char* model_path, uint64_t* out16);
 APRIL_EXPORT const char* aab_engine_version(void);
 
 #ifdef __cplusplus

@@ -140,31 +140,78 @@ def calibrate(W, d, vocab, seed):
 
 
 # ----------------------------------------------------------------------------- ONNX graphs
+# Two independently structured writers of the SAME network (the real exporter's output is not available here, so the loader is
+# exercised against both): style "a" = MatMul(x, W^T) + Add(bias, y) for nn.Linear, Gemm(transB=1) for the LSTM gate projections
+# (W_ih first), scalars as Constant nodes, torch-like parameter names; style "b" = Gemm on squeezed 2-D operands for nn.Linear,
+# MatMul + Add(y, bias) for the gate projections with W_hh emitted BEFORE W_ih, W_hr as a bias-free Gemm, every initializer
+# anonymous ("onnx::Gemm_123" / bare numbers), scalars as initializers, outputs named directly (no Identity nodes).
+STYLE = {"v": "a"}
+
+
+def _scalar(g, arr):
+    if STYLE["v"] == "b":
+        return g.init(np.asarray(arr), str(900000 + len(g.inits)))
+    return g.const(arr)
+
+
+def _pname(g, torch_name, kind="Const"):
+    return g.fresh("onnx::%s" % kind) if STYLE["v"] == "b" else torch_name
+
+
 def _double_swish(g, x):
-    one = g.const(np.array(1.0, np.float32))
+    one = _scalar(g, np.array(1.0, np.float32))
     s = g.op("Sub", [x, one])
     s = g.op("Sigmoid", [s])
-    return g.op("Mul", [x, s])
+    return g.op("Mul", [s, x] if STYLE["v"] == "b" else [x, s])
 
 
 def _basic_norm(g, x, eps):
-    two = g.const(np.array(2.0, np.float32))
+    two = _scalar(g, np.array(2.0, np.float32))
     p = g.op("Pow", [x, two])
     m = g.op("ReduceMean", [p], axes=[-1], keepdims=1)
-    e = g.const(np.array(eps, np.float32))
-    a = g.op("Add", [m, e])
-    mh = g.const(np.array(-0.5, np.float32))
+    e = _scalar(g, np.array(eps, np.float32))
+    a = g.op("Add", [e, m] if STYLE["v"] == "b" else [m, e])
+    mh = _scalar(g, np.array(-0.5, np.float32))
     s = g.op("Pow", [a, mh])
     return g.op("Mul", [x, s])
 
 
-def _linear3d(g, x, w, b):
-    """nn.Linear on a 3-D tensor -> MatMul(x, W^T const) + Add(bias) (torch exporter convention)."""
+def _linear3d(g, x, w, b, out_name=None):
+    """nn.Linear on a 3-D tensor. Style a: MatMul(x, W^T const) + Add(bias, y) (torch exporter convention);
+    style b: Squeeze -> Gemm(x2, W, bias, transB=1) -> Unsqueeze."""
+    names = [out_name] if out_name else None
+    if STYLE["v"] == "b":
+        x2 = g.op("Squeeze", [x], axes=[0])
+        ins = [x2, g.init(w, g.fresh("onnx::Gemm"))] + ([g.init(b, g.fresh("onnx::Gemm"))] if b is not None else [])
+        y2 = g.op("Gemm", ins, alpha=1.0, beta=1.0, transB=1)
+        return g.op("Unsqueeze", [y2], axes=[0], out_names=names)
     wt = g.init(np.ascontiguousarray(w.T), g.fresh("onnx::MatMul"))
-    y = g.op("MatMul", [x, wt])
     if b is None:
-        return y
-    return g.op("Add", [g.init(b, g.fresh("bias")), y])
+        return g.op("MatMul", [x, wt], out_names=names)
+    y = g.op("MatMul", [x, wt])
+    return g.op("Add", [g.init(b, g.fresh("bias")), y], out_names=names)
+
+
+def _gate_projections(g, x2, h2, W, p, l):
+    """(W_ih x + b_ih) + (W_hh h + b_hh) for one layer; returns the summed gate pre-activations (1, 4H)."""
+    if STYLE["v"] == "b":
+        whh = g.init(np.ascontiguousarray(W[p + "w_hh"].T), g.fresh("onnx::MatMul"))
+        gh = g.op("Add", [g.op("MatMul", [h2, whh]), g.init(W[p + "b_hh"], g.fresh("onnx::Add"))])
+        wih = g.init(np.ascontiguousarray(W[p + "w_ih"].T), g.fresh("onnx::MatMul"))
+        gi = g.op("Add", [g.op("MatMul", [x2, wih]), g.init(W[p + "b_ih"], g.fresh("onnx::Add"))])
+        return g.op("Add", [gh, gi])
+    wih = g.init(W[p + "w_ih"], "encoder.encoder.layers.%d.lstm.weight_ih_l0" % l)
+    bih = g.init(W[p + "b_ih"], "encoder.encoder.layers.%d.lstm.bias_ih_l0" % l)
+    whh = g.init(W[p + "w_hh"], "encoder.encoder.layers.%d.lstm.weight_hh_l0" % l)
+    bhh = g.init(W[p + "b_hh"], "encoder.encoder.layers.%d.lstm.bias_hh_l0" % l)
+    gi = g.op("Gemm", [x2, wih, bih], alpha=1.0, beta=1.0, transB=1)
+    gh = g.op("Gemm", [h2, whh, bhh], alpha=1.0, beta=1.0, transB=1)
+    return g.op("Add", [gi, gh])
+
+
+def _output(g, x, name):
+    if STYLE["v"] != "b":
+        g.op("Identity", [x], out_names=[name])
 
 
 def build_encoder(W, d):
@@ -175,14 +222,14 @@ def build_encoder(W, d):
     g.add_input("c", ox.FLOAT, [L, 1, H])
     x = g.op("Unsqueeze", ["x"], axes=[1])
     for i, stride in ((1, 1), (2, 2), (3, 2)):
-        w = g.init(W["conv%d_w" % i], "encoder.encoder_embed.conv.%d.weight" % ((i - 1) * 3))
-        b = g.init(W["conv%d_b" % i], "encoder.encoder_embed.conv.%d.bias" % ((i - 1) * 3))
+        w = g.init(W["conv%d_w" % i], _pname(g, "encoder.encoder_embed.conv.%d.weight" % ((i - 1) * 3), "Conv"))
+        b = g.init(W["conv%d_b" % i], _pname(g, "encoder.encoder_embed.conv.%d.bias" % ((i - 1) * 3), "Conv"))
         x = g.op("Conv", [x, w, b], dilations=[1, 1], group=1, kernel_shape=[3, 3],
                  pads=[0, 0, 0, 0], strides=[stride, stride])
         x = _double_swish(g, x)
     x = g.op("Transpose", [x], perm=[0, 2, 1, 3])
     f3 = ((d["MEL"] - 3) // 2 - 1) // 2
-    shp = g.const(np.array([1, 1, 128 * f3], np.int64))
+    shp = _scalar(g, np.array([1, 1, W["conv3_w"].shape[0] * f3], np.int64))
     x = g.op("Reshape", [x, shp])
     x = _linear3d(g, x, W["out_w"], W["out_b"])
     x = _basic_norm(g, x, float(W["out_norm_eps"]))
@@ -199,13 +246,7 @@ def build_encoder(W, d):
         h2 = g.op("Squeeze", [hl], axes=[0])                         # (1, D)
         c2 = g.op("Squeeze", [cl], axes=[0])                         # (1, H)
         x2 = g.op("Squeeze", [x], axes=[0])                          # (1, D)
-        wih = g.init(W[p + "w_ih"], "encoder.encoder.layers.%d.lstm.weight_ih_l0" % l)
-        bih = g.init(W[p + "b_ih"], "encoder.encoder.layers.%d.lstm.bias_ih_l0" % l)
-        whh = g.init(W[p + "w_hh"], "encoder.encoder.layers.%d.lstm.weight_hh_l0" % l)
-        bhh = g.init(W[p + "b_hh"], "encoder.encoder.layers.%d.lstm.bias_hh_l0" % l)
-        gi = g.op("Gemm", [x2, wih, bih], alpha=1.0, beta=1.0, transB=1)
-        gh = g.op("Gemm", [h2, whh, bhh], alpha=1.0, beta=1.0, transB=1)
-        gates = g.op("Add", [gi, gh])
+        gates = _gate_projections(g, x2, h2, W, p, l)
         i_, f_, g_, o_ = g.op("Split", [gates], n_out=4, axis=1, split=[H, H, H, H])
         i_ = g.op("Sigmoid", [i_])
         f_ = g.op("Sigmoid", [f_])
@@ -213,8 +254,11 @@ def build_encoder(W, d):
         o_ = g.op("Sigmoid", [o_])
         cn = g.op("Add", [g.op("Mul", [f_, c2]), g.op("Mul", [i_, g_])])
         m = g.op("Mul", [o_, g.op("Tanh", [cn])])
-        whr = g.init(np.ascontiguousarray(W[p + "w_hr"].T), g.fresh("onnx::MatMul"))
-        hn = g.op("MatMul", [m, whr])                                # (1, D)
+        if STYLE["v"] == "b":
+            hn = g.op("Gemm", [m, g.init(W[p + "w_hr"], g.fresh("onnx::Gemm"))], alpha=1.0, beta=1.0, transB=1)
+        else:
+            whr = g.init(np.ascontiguousarray(W[p + "w_hr"].T), g.fresh("onnx::MatMul"))
+            hn = g.op("MatMul", [m, whr])                            # (1, D)
         hs.append(g.op("Unsqueeze", [hn], axes=[0]))
         cs.append(g.op("Unsqueeze", [cn], axes=[0]))
         x = g.op("Add", [hs[-1], x])                                 # src = dropout(src_lstm) + src
@@ -224,8 +268,8 @@ def build_encoder(W, d):
         x = g.op("Add", [x, ff])
         x = _basic_norm(g, x, float(W[p + "norm_eps"]))
     x = g.op("Transpose", [x], perm=[1, 0, 2])
-    x = _linear3d(g, x, W["enc_proj_w"], W["enc_proj_b"])
-    g.op("Identity", [x], out_names=["encoder_out"])
+    x = _linear3d(g, x, W["enc_proj_w"], W["enc_proj_b"], out_name="encoder_out" if STYLE["v"] == "b" else None)
+    _output(g, x, "encoder_out")
     g.op("Concat", hs, out_names=["next_h"], axis=0)
     g.op("Concat", cs, out_names=["next_c"], axis=0)
     g.add_output("encoder_out", ox.FLOAT, [1, 1, d["J"]])
@@ -237,15 +281,15 @@ def build_encoder(W, d):
 def build_decoder(W, d):
     g = ox.GraphBuilder("torch_jit")
     g.add_input("context", ox.INT64, [1, d["CTX"]])
-    emb = g.init(W["emb"], "decoder.embedding.weight")
+    emb = g.init(W["emb"], _pname(g, "decoder.embedding.weight", "Gather"))
     e = g.op("Gather", [emb, "context"], axis=0)                     # (1, CTX, E)
     e = g.op("Transpose", [e], perm=[0, 2, 1])                       # (1, E, CTX)
-    cw = g.init(W["dec_conv_w"], "decoder.conv.weight")
+    cw = g.init(W["dec_conv_w"], _pname(g, "decoder.conv.weight", "Conv"))
     e = g.op("Conv", [e, cw], dilations=[1], group=d["E"], kernel_shape=[d["CTX"]], pads=[0, 0], strides=[1])
     e = g.op("Transpose", [e], perm=[0, 2, 1])                       # (1, 1, E)
     e = g.op("Relu", [e])
-    y = _linear3d(g, e, W["dec_proj_w"], W["dec_proj_b"])
-    g.op("Identity", [y], out_names=["decoder_out"])
+    y = _linear3d(g, e, W["dec_proj_w"], W["dec_proj_b"], out_name="decoder_out" if STYLE["v"] == "b" else None)
+    _output(g, y, "decoder_out")
     g.add_output("decoder_out", ox.FLOAT, [1, 1, d["J"]])
     return g.serialize()
 
@@ -256,8 +300,8 @@ def build_joiner(W, d):
     g.add_input("decoder_out", ox.FLOAT, [1, 1, d["J"]])
     s = g.op("Add", ["encoder_out", "decoder_out"])
     s = g.op("Tanh", [s])
-    y = _linear3d(g, s, W["join_w"], W["join_b"])
-    g.op("Identity", [y], out_names=["logits"])
+    y = _linear3d(g, s, W["join_w"], W["join_b"], out_name="logits" if STYLE["v"] == "b" else None)
+    _output(g, y, "logits")
     g.add_output("logits", ox.FLOAT, [1, 1, d["V"]])
     return g.serialize()
 
@@ -298,7 +342,9 @@ def write_april(path, nets, params, name, desc, lang="en-us"):
         f.write(params)
 
 
-def generate(path, preset="tiny", seed=1234, calibrated=True, save_npz=None):
+def generate(path, preset="tiny", seed=1234, calibrated=True, save_npz=None, style="a"):
+    """style: which of the two graph writers emits the three ONNX graphs (same weights, same arithmetic)."""
+    STYLE["v"] = style
     d = PRESETS[preset]
     rs = np.random.RandomState(seed + 1)
     vocab = make_vocab(d["V"], rs)
@@ -306,6 +352,7 @@ def generate(path, preset="tiny", seed=1234, calibrated=True, save_npz=None):
     if calibrated:
         W = calibrate(W, d, vocab, seed)
     nets = [build_encoder(W, d), build_decoder(W, d), build_joiner(W, d)]
+    STYLE["v"] = "a"
     write_april(path, nets, params_block(d, vocab),
                 "synthetic-%s-seed%d" % (preset, seed),
                 "Synthetic random-weight lstm_transducer_stateless2 (%s dims) for parity tests" % preset)
@@ -321,8 +368,9 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--npz", default=None)
     ap.add_argument("--no-calibrate", action="store_true")
+    ap.add_argument("--style", default="a", choices=["a", "b"])
     a = ap.parse_args()
-    generate(a.out, a.preset, a.seed, not a.no_calibrate, a.npz)
+    generate(a.out, a.preset, a.seed, not a.no_calibrate, a.npz, a.style)
     print("wrote", a.out, os.path.getsize(a.out), "bytes")
 
 
