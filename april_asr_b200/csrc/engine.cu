@@ -392,7 +392,6 @@ public:
         fp.pad_value = (float)log((double)1.1920928955078125e-07f);
         fp.window = upload(win); fp.twiddle = upload(tw); fp.mel_start = upload(ms); fp.mel_count = upload(mc); fp.mel_off = upload(mo); fp.mel_w = upload(mw);
         CK(cudaFuncSetAttribute(k::fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * N * (int)sizeof(double)));
-        CK(cudaFuncSetAttribute(k::fbank_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * N * (int)sizeof(double)));
 
         cp.SEG = d.SEG; cp.MEL = d.MEL; cp.STEP = d.STEP; cp.C1 = d.C1; cp.C2 = d.C2; cp.C3 = d.C3;
         cp.T1 = d.SEG - 2; cp.F1 = d.MEL - 2; cp.T2 = (cp.T1 - 3) / 2 + 1; cp.F2 = (cp.F1 - 3) / 2 + 1; cp.F3 = d.F3;
@@ -874,7 +873,9 @@ public:
         }
     }
 
-    static bool fbank_v2() { static const bool v = getenv("APRIL_B200_FBANK") && !strcmp(getenv("APRIL_B200_FBANK"), "v2"); return v; }   // opt-in until its speed is measured
+    // the radix-8 front-end serves the 512-sample window (every model of the reference: 25 ms at 16 kHz); other windows take the generic kernel
+    bool fbank512() const { static const bool generic = getenv("APRIL_B200_FBANK") && !strcmp(getenv("APRIL_B200_FBANK"), "generic"); return frame_N == k::FB3_N && !generic; }
+    static constexpr size_t kFbank512Smem = 4 * 2 * k::FB3_PITCH * sizeof(double);
 
     template <int NP, int EPI, int CL> void gemm_tc_launch(unsigned grid, const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, const tc::GemmArgs& g) {
         bool& attr_done = gemm_attr[(NP == 3 ? 8 : 0) + EPI * 2 + (CL - 1)];   // per engine (= per device) and instantiation
@@ -960,7 +961,7 @@ public:
         CK(cudaMemcpyAsync((char*)b_meta.p + 32, &off, sizeof off, cudaMemcpyHostToDevice, st));
         b_fb.ensure(sizeof(float) * (size_t)nf * d.MEL);
         int* dm = b_meta.as<int>();
-        if (fbank_v2()) k::fbank_kernel_v2<<<dim3((unsigned)((nf + 31) / 32), 1), 128, (size_t)4 * 3 * frame_N * sizeof(double), st>>>(
+        if (fbank512()) k::fbank512_kernel<<<dim3((unsigned)((nf + 3) / 4), 1), 128, kFbank512Smem, st>>>(
             fp, b_pcm.as<int16_t>(), reinterpret_cast<long long*>((char*)b_meta.p + 32), dm, dm + 1, dm + 2, dm + 3, b_fb.as<float>(), nf);
         else k::fbank_kernel<<<dim3((unsigned)((nf + 3) / 4), 1), 128, (size_t)4 * 3 * frame_N * sizeof(double), st>>>(
             fp, b_pcm.as<int16_t>(), reinterpret_cast<long long*>((char*)b_meta.p + 32), dm, dm + 1, dm + 2, dm + 3, b_fb.as<float>(), nf);
@@ -1092,9 +1093,9 @@ public:
         span_begin(4);
         k::carry_in_kernel<<<B, 128, 0, st>>>(carry_store, d_slot, d_carry, FB, row_pitch, MEL, CARRY_CAP); launch_check();
         if (max_new > 0) {
-            if (fbank_v2()) {
-                dim3 grid((unsigned)((max_new + 31) / 32), (unsigned)B);
-                k::fbank_kernel_v2<<<grid, 128, (size_t)4 * 3 * N * sizeof(double), st>>>(fp, b_pcm.as<int16_t>(), d_off, d_padb, d_nfr, d_nnew, d_carry, FB, row_pitch);
+            if (fbank512()) {
+                dim3 grid((unsigned)((max_new + 3) / 4), (unsigned)B);
+                k::fbank512_kernel<<<grid, 128, kFbank512Smem, st>>>(fp, b_pcm.as<int16_t>(), d_off, d_padb, d_nfr, d_nnew, d_carry, FB, row_pitch);
             } else {
                 dim3 grid((unsigned)((max_new + 3) / 4), (unsigned)B);
                 k::fbank_kernel<<<grid, 128, (size_t)4 * 3 * N * sizeof(double), st>>>(fp, b_pcm.as<int16_t>(), d_off, d_padb, d_nfr, d_nnew, d_carry, FB, row_pitch);

@@ -154,106 +154,169 @@ fbank_kernel(FbankParams P, const int16_t* __restrict__ pcm, const long long* __
     }
 }
 
-// Variant (opt-in with APRIL_B200_FBANK=v2: bit-compatible on hardware, speed not yet measured; same arithmetic, same order): the DC sum is a
-// 512-step serial chain (float accumulator over double data, fbank.c:241-246) that fbank_kernel runs on ONE lane per frame
-// (ncu: 6150 warp instructions per frame, issue-active 26 %). Here a warp owns 8 consecutive rows: lanes 0-7 run the
-// eight serial chains side by side (reading the PCM through L1), then the warp processes its rows one after the other.
-// grid (ceil(max_new_rows / 32), B), block 128.
-constexpr int FB2_RPW = 8;
+// ------------------------------------------------------------------------------------------------
+// F1/F2 for the 512-sample window every shipped model uses (25 ms at 16 kHz, rounded to a power of two): same arithmetic
+// as fbank_kernel wherever the reference's rounding is visible (DC mean, pre-emphasis, window, float power, sequential
+// float mel sums, double log), restructured where it is not:
+//  * the DC sum. fbank.c:241-246 accumulates 512 doubles into a FLOAT. Every sample is int16 / 32768 (a multiple of 2^-15,
+//    april_session.c:520-522) and every partial sum is below 512 in magnitude, i.e. k * 2^-15 with |k| <= 2^24: exactly
+//    representable in a float. The 512-step serial chain therefore never rounds, and equals the INTEGER sum of the samples,
+//    which a warp reduces in five shuffles. (fbank_kernel runs the chain on one lane: 1 500 of its 6 150 instructions per frame.)
+//  * the FFT: 512 = 8 x 8 x 8, three decimation-in-frequency radix-8 passes in fp64 with the butterflies in registers
+//    (three shared-memory round trips instead of nine, rows padded by two doubles per eight so that the stride-8 and the
+//    16-byte accesses are conflict-free), real input in the first pass, and only bins 0..255 (half of the last pass' outputs)
+//    are formed. pocketfft (fbank.c:259-270) computes the same DFT in double; any two correct fp64 FFTs agree to ~1e-16
+//    relative, far below the float rounding of the power that follows.
+// One warp per frame, 4 frames per CTA. grid (ceil(max_new_rows / 4), B), block 128.
+// ------------------------------------------------------------------------------------------------
+constexpr int FB3_N = 512;
+constexpr int FB3_PITCH = FB3_N + 2 * (FB3_N / 8);                         // doubles per padded array
+__device__ __forceinline__ int fb3_phys(int i) { return i + 2 * (i >> 3); }
+
+struct cplx { double x, y; };
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return { a.x + b.x, a.y + b.y }; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return { a.x - b.x, a.y - b.y }; }
+__device__ __forceinline__ cplx cmul(cplx a, cplx w) { return { a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x }; }
+__device__ __forceinline__ cplx cmul_mi(cplx a) { return { a.y, -a.x }; }   // a * (-i)
+
+// forward 8-point DFT in place: y[m] = sum_k x[k] exp(-2 pi i m k / 8)
+__device__ __forceinline__ void dft8(cplx (&v)[8]) {
+    const double r = 0.70710678118654752440;
+    cplx a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+    cplx b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+    b1 = { (b1.x + b1.y) * r, (b1.y - b1.x) * r };                          // * W8^1 = (1 - i) / sqrt 2
+    b2 = cmul_mi(b2);                                                       // * W8^2 = -i
+    b3 = { (b3.y - b3.x) * r, -(b3.x + b3.y) * r };                         // * W8^3 = (-1 - i) / sqrt 2
+    // even outputs: DFT4 of a;  odd outputs: DFT4 of b
+    cplx t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
+    v[0] = cadd(t0, t2); v[4] = csub(t0, t2); v[2] = cadd(t1, t3); v[6] = csub(t1, t3);
+    cplx u0 = cadd(b0, b2), u1 = csub(b0, b2), u2 = cadd(b1, b3), u3 = cmul_mi(csub(b1, b3));
+    v[1] = cadd(u0, u2); v[5] = csub(u0, u2); v[3] = cadd(u1, u3); v[7] = csub(u1, u3);
+}
+// W_512^idx from the half table (cos, -sin)(2 pi k / 512), k < 256
+__device__ __forceinline__ cplx fb3_tw(const double2* __restrict__ tw, int idx) {
+    idx &= FB3_N - 1;
+    const double2 w = __ldg(tw + (idx & (FB3_N / 2 - 1)));
+    return idx >= FB3_N / 2 ? cplx{ -w.x, -w.y } : cplx{ w.x, w.y };
+}
+
 __global__ void __launch_bounds__(128)
-fbank_kernel_v2(FbankParams P, const int16_t* __restrict__ pcm, const long long* __restrict__ pcm_off,
+fbank512_kernel(FbankParams P, const int16_t* __restrict__ pcm, const long long* __restrict__ pcm_off,
                 const int* __restrict__ pad_before, const int* __restrict__ n_frames, const int* __restrict__ n_new,
                 const int* __restrict__ carry, float* __restrict__ FB, int row_pitch) {
     extern __shared__ double smem_d[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int r_first = (blockIdx.x * 4 + warp) * FB2_RPW;
-    const int nn = n_new[b], pb = pad_before[b], nf = n_frames[b];
-    if (r_first >= nn) return;
-    const int N = P.N;
-    double* dat = smem_d + (size_t)warp * 3 * N;
-    double* re = dat + N;
-    double* im = re + N;
-    const int16_t* xb = pcm + pcm_off[b];
+    const int r = blockIdx.x * 4 + warp;
+    if (r >= n_new[b]) return;
+    float* out = FB + ((size_t)b * row_pitch + carry[b] + r) * P.mel;
+    const int pb = pad_before[b];
+    const int src = (r >= pb && r < pb + n_frames[b]) ? r - pb : -1;
+    if (src < 0) {                                   // fbank_flush pad rows, fbank.c:312-316
+        for (int m = lane; m < P.mel; m += 32) out[m] = P.pad_value;
+        return;
+    }
+    double* re = smem_d + (size_t)warp * 2 * FB3_PITCH;
+    double* im = re + FB3_PITCH;
+    const int16_t* x = pcm + pcm_off[b] + (long long)src * P.shift;
 
-    // the eight DC means of this warp's rows, one serial chain per lane
-    float mean_l = 0.f;
-    if (lane < FB2_RPW) {
-        const int r = r_first + lane;
-        if (r < nn && r >= pb && r < pb + nf) {
-            const int16_t* x = xb + (long long)(r - pb) * P.shift;
-            float sum = 0.f;
-            for (int j = 0; j < N; j++) sum = (float)((double)sum + (double)((float)x[j] / 32768.0f));
-            mean_l = sum / (float)N;
+    // samples j = 16 lane + u: pcm_off is a multiple of 8 samples, shift * 2 bytes a multiple of 16 whenever shift is a multiple of 8
+    short xs[16];
+    if ((P.shift & 7) == 0) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(x + 16 * lane)), hi = __ldg(reinterpret_cast<const uint4*>(x + 16 * lane + 8));
+        const uint32_t wds[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+#pragma unroll
+        for (int u = 0; u < 8; u++) { xs[2 * u] = (short)(wds[u] & 0xFFFFu); xs[2 * u + 1] = (short)(wds[u] >> 16); }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 16; u++) xs[u] = x[16 * lane + u];
+    }
+    int isum = 0;
+#pragma unroll
+    for (int u = 0; u < 16; u++) isum += (int)xs[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+    const float mean = ((float)isum / 32768.0f) / (float)FB3_N;            // == the reference's float chain (exact, see above), then its float division
+    const double dmean = (double)mean;
+    const double coeff = (double)0.97f;                                     // preemph_coeff is a float, fbank.c:188
+    // data[j] = ((x[j] - mean) - 0.97 (x[j-1] - mean)) * window[j]; j = 0 uses itself as predecessor (fbank.c:249-257)
+    const short x_prev_lane = (short)__shfl_up_sync(0xffffffffu, (int)xs[15], 1);
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        const int j = 16 * lane + u;
+        const short xp = u > 0 ? xs[u - 1] : (lane > 0 ? x_prev_lane : xs[0]);
+        const double cur = __dsub_rn((double)((float)xs[u] / 32768.0f), dmean);
+        const double prev = __dsub_rn((double)((float)xp / 32768.0f), dmean);
+        double v = __dsub_rn(cur, __dmul_rn(coeff, prev));
+        v = __dmul_rn(v, (double)__ldg(P.window + j));
+        re[fb3_phys(j)] = v;
+    }
+    __syncwarp();
+    // ---- pass 1: span 64, real input. butterfly j: x_k = data[j + 64 k]; y_m *= W512^(j m); -> position j + 64 m
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        const int j = lane + 32 * it;
+        cplx v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = { re[fb3_phys(j + 64 * k)], 0.0 };
+        dft8(v);
+#pragma unroll
+        for (int m = 1; m < 8; m++) v[m] = cmul(v[m], fb3_tw(P.twiddle, j * m));
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 8; m++) { re[fb3_phys(j + 64 * m)] = v[m].x; im[fb3_phys(j + 64 * m)] = v[m].y; }
+    }
+    __syncwarp();
+    // ---- pass 2: span 8 inside blocks of 64. butterfly (blk, j): x_k = a[64 blk + j + 8 k]; y_m *= W64^(j m) = W512^(8 j m)
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        const int id = lane + 32 * it, blk = id >> 3, j = id & 7;
+        cplx v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int p = fb3_phys(64 * blk + j + 8 * k); v[k] = { re[p], im[p] }; }
+        dft8(v);
+#pragma unroll
+        for (int m = 1; m < 8; m++) v[m] = cmul(v[m], fb3_tw(P.twiddle, 8 * j * m));
+#pragma unroll
+        for (int m = 0; m < 8; m++) { const int p = fb3_phys(64 * blk + j + 8 * m); re[p] = v[m].x; im[p] = v[m].y; }   // a butterfly only rewrites what it read
+    }
+    __syncwarp();
+    // ---- pass 3: span 1. block q = 8 m1 + m2 holds, after its DFT8, X[m1 + 8 m2 + 64 m3] in element m3: bins < 256 are m3 < 4.
+    // power in FLOAT, im[0] forced to 0 (fbank.c:269-280); written over the (no longer needed) start of `re` region of ANOTHER array: pw
+    float* pw = reinterpret_cast<float*>(im);                               // im rows are consumed below before pw overwrites them: see the sync
+    float pwr[2][4];
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int q = lane + 32 * it;
+        cplx v[8];
+        const double2* rp = reinterpret_cast<const double2*>(re + fb3_phys(8 * q));
+        const double2* ip = reinterpret_cast<const double2*>(im + fb3_phys(8 * q));
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const double2 a = rp[k], c = ip[k]; v[2 * k] = { a.x, c.x }; v[2 * k + 1] = { a.y, c.y }; }
+        dft8(v);
+#pragma unroll
+        for (int m3 = 0; m3 < 4; m3++) {
+            const int kbin = (q >> 3) + 8 * (q & 7) + 64 * m3;
+            const float fr = (float)v[m3].x, fi = kbin == 0 ? 0.f : (float)v[m3].y;
+            pwr[it][m3] = __fadd_rn(__fmul_rn(fr, fr), __fmul_rn(fi, fi));
         }
     }
-    for (int k = 0; k < FB2_RPW; k++) {
-        const int r = r_first + k;
-        if (r >= nn) break;                                              // warp-uniform
-        float* out = FB + ((size_t)b * row_pitch + carry[b] + r) * P.mel;
-        const float mean = __shfl_sync(0xffffffffu, mean_l, k);
-        if (!(r >= pb && r < pb + nf)) {                                 // fbank_flush pad rows, fbank.c:312-316
-            for (int m = lane; m < P.mel; m += 32) out[m] = P.pad_value;
-            continue;
-        }
-        const int16_t* x = xb + (long long)(r - pb) * P.shift;
-        for (int j = lane; j < N; j += 32) dat[j] = (double)((float)x[j] / 32768.0f);
-        __syncwarp();
-        const double dmean = (double)mean;
-        const double coeff = (double)0.97f;
-        for (int base = 0; base < N; base += 32 * 8) {
-            double cur[8], prev[8];
+    __syncwarp();                                                           // every lane has read its rows of re / im
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                int j = base + u * 32 + lane;
-                cur[u] = __dsub_rn(dat[j], dmean);
-                prev[u] = __dsub_rn(dat[j > 0 ? j - 1 : 0], dmean);
-            }
-            __syncwarp();
+    for (int it = 0; it < 2; it++) {
+        const int q = lane + 32 * it;
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                int j = base + u * 32 + lane;
-                double v = __dsub_rn(cur[u], __dmul_rn(coeff, prev[u]));
-                v = __dmul_rn(v, (double)P.window[j]);
-                int rj = __brev((unsigned)j) >> (32 - P.log2N);
-                re[rj] = v;
-                im[rj] = 0.0;
-            }
-            __syncwarp();
-        }
-        for (int s = 1; s <= P.log2N; s++) {
-            const int half = 1 << (s - 1);
-            const int tw_stride = N >> s;
-            for (int j = lane; j < N / 2; j += 32) {
-                int pos = j & (half - 1);
-                int i0 = ((j >> (s - 1)) << s) + pos;
-                int i1 = i0 + half;
-                double2 w = P.twiddle[pos * tw_stride];
-                double xr = re[i1], xi = im[i1];
-                double tr = w.x * xr - w.y * xi;
-                double ti = w.x * xi + w.y * xr;
-                double ar = re[i0], ai = im[i0];
-                re[i0] = ar + tr; im[i0] = ai + ti;
-                re[i1] = ar - tr; im[i1] = ai - ti;
-            }
-            __syncwarp();
-        }
-        float* pw = (float*)dat;
-        for (int kbin = lane; kbin < P.nbins; kbin += 32) {
-            float fr = (float)re[kbin];
-            float fi = kbin == 0 ? 0.f : (float)im[kbin];
-            pw[kbin] = __fadd_rn(__fmul_rn(fr, fr), __fmul_rn(fi, fi));
-        }
-        __syncwarp();
-        for (int m = lane; m < P.mel; m += 32) {
-            const int k0 = P.mel_start[m], cnt = P.mel_count[m];
-            const float* w = P.mel_w + P.mel_off[m];
-            float val = 0.f;
-            for (int i = 0; i < cnt; i++) val = __fadd_rn(val, __fmul_rn(pw[k0 + i], w[i]));
-            const float kEps = 1.1920928955078125e-07f;
-            out[m] = (float)log((double)fmaxf(kEps, val));
-        }
-        __syncwarp();                                                    // dat / re / im are reused by the next row
+        for (int m3 = 0; m3 < 4; m3++) pw[(q >> 3) + 8 * (q & 7) + 64 * m3] = pwr[it][m3];
+    }
+    __syncwarp();
+    // mel: sequential float sum over fft bins (zero weights contribute exact +0), fbank.c:283-296
+    for (int m = lane; m < P.mel; m += 32) {
+        const int k0 = P.mel_start[m], cnt = P.mel_count[m];
+        const float* w = P.mel_w + P.mel_off[m];
+        float val = 0.f;
+        for (int i = 0; i < cnt; i++) val = __fadd_rn(val, __fmul_rn(pw[k0 + i], __ldg(w + i)));
+        const float kEps = 1.1920928955078125e-07f;
+        out[m] = (float)log((double)fmaxf(kEps, val));
     }
 }
 

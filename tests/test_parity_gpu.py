@@ -70,10 +70,14 @@ def test_encoder_out_and_logits_within_tolerance():
 
 
 def test_chunk_size_invariance_and_streaming_equals_bulk():
+    """Any chunking of the same stream must give the ORACLE's callbacks for it (the oracle itself is chunking-invariant:
+    tests/test_oracle.py::test_oracle_chunk_size_invariance)."""
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
     pcm = C.gen_stream(9, 64000)
-    base = C.run_product_batch(C.TINY_MODEL, [pcm])[0].keys()
-    for chunk in (640, 3200, 7001):
-        assert C.run_product_batch(C.TINY_MODEL, [pcm], chunk=chunk)[0].keys() == base
+    want = C.run_oracle(C.TINY_MODEL, pcm).keys()
+    for chunk in (None, 640, 3200, 7001):
+        assert C.run_product_batch(C.TINY_MODEL, [pcm], chunk=chunk)[0].keys() == want, "chunk %s" % chunk
 
 
 def test_single_session_reference_api_and_flush_idempotence():
@@ -128,29 +132,6 @@ def test_full_size_model_matches_oracle_tokens():
         assert c.keys() == o.keys()
 
 
-def test_async_session_batcher():
-    import time
-    lib = C.product_lib()
-    m = A.Model(C.TINY_MODEL, lib)
-    cols = [C.Collected() for _ in range(4)]
-    ss = [A.Session(m, c.cb, asynchronous=True, no_rt=True) for c in cols]
-    pcms = [C.gen_stream(30 + i, 48000) for i in range(4)]
-    for i in range(0, 48000, 1600):
-        for s, p in zip(ss, pcms):
-            s.feed_pcm16(p[i:i + 1600])
-        time.sleep(0.002)
-    time.sleep(0.3)
-    for s in ss:
-        s.flush()
-    time.sleep(0.5)
-    sync = C.run_product_batch(C.TINY_MODEL, pcms, model=m)
-    for a, b in zip(cols, sync):
-        assert [k for k in a.keys() if k[0] != 3] == b.keys()
-    for s in ss:
-        s.close()
-    m.close()
-
-
 @pytest.mark.parametrize("prog", ["example", "example_srt"])
 def test_reference_example_cpp_unmodified_against_this_library(tmp_path, prog):
     """/root/reference/example.cpp and example_srt.cpp compiled UNMODIFIED twice (oracle/Makefile): against the oracle library
@@ -173,13 +154,13 @@ def test_reference_example_cpp_unmodified_against_this_library(tmp_path, prog):
         assert b"Model name: synthetic-tiny" in b.stdout
 
 
-def _oracle_many(model, pcms, threads=8):
+def _oracle_many(model, pcms, threads=8, chunk=None):
     import threading
     out = [None] * len(pcms)
 
     def work(k):
         for i in range(k, len(pcms), threads):
-            out[i] = C.run_oracle(model, pcms[i])
+            out[i] = C.run_oracle(model, pcms[i], chunk=chunk)
     ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
     for t in ts: t.start()
     for t in ts: t.join()
@@ -197,21 +178,85 @@ def test_several_sessions_per_search_cluster():
     assert not bad, "sessions with differing callbacks: %s" % bad
 
 
+_ORACLE_30S = {}
+
+
+def _oracle_30s(path, ids):
+    """Oracle callback logs of the 30 s benchmark streams, computed once per test session and shared between the tests below."""
+    todo = [i for i in ids if i not in _ORACLE_30S]
+    if todo:
+        res = _oracle_many(path, [C.gen_stream(i, 16000 * 30) for i in todo], threads=min(len(todo), 24))
+        for i, r in zip(todo, res):
+            _ORACLE_30S[i] = r
+    return [_ORACLE_30S[i] for i in ids]
+
+
+# Two fp32-grade implementations of an 84 M-parameter recurrent network agree on raw logits to ~1e-4, not to the last bit, so a
+# greedy decision whose margin is smaller than that can fall either way. Measured (tools/precision_study.py, DESIGN.md section 2):
+# about one such decision per 30 000; it changes one TENTATIVE token of one partial result and nothing after it. FINAL results
+# must be identical on every checked stream; whole callback logs must be identical on all but at most this many streams.
+MAX_STREAMS_WITH_A_NEAR_TIE = 1
+CHECKED_STREAMS = 24
+
+
+def _check_against_oracle(got, want, ids, what):
+    diffs = [C.callback_diff(got[i], w) for i, w in zip(ids, want)]
+    bad = [i for i, w in zip(ids, want) if got[i].keys() != w.keys()]
+    print("%s: %d of %d checked sessions identical; differing: %s; (callbacks differing, finals identical): %s" % (what, len(ids) - len(bad), len(ids), bad, [d for d in diffs if d[0]]))
+    assert all(f for _, f in diffs), "%s: final results differ" % what
+    assert all(n <= 2 for n, _ in diffs), "%s: more than a tentative token differs" % what
+    assert len(bad) <= MAX_STREAMS_WITH_A_NEAR_TIE, "%s: callback logs differ on sessions %s" % (what, bad)
+
+
 def test_full_length_batch_matches_reference():
-    """BASELINE configs[1] at full size: 64 sessions x 30 s through the batched path; the first 12 sessions are also run
-    through the oracle (30 s each, one thread per session). The whole callback sequence (partials, finals, silences, token
-    ids, flags, times) must be identical; one near-tied decision in 12 long streams is tolerated and reported, because two
-    fp32 implementations that differ by 1e-5 in a logit cannot agree on a margin smaller than that."""
+    """BASELINE configs[1] at full size: 64 sessions x 30 s through the batched path; 24 of them are also run through the
+    oracle (30 s each, one thread per session). The whole callback sequence (partials, finals, silences, token ids, flags,
+    times) is compared."""
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
     path = C.model_path("full")
     pcms = [C.gen_stream(i, 16000 * 30) for i in range(64)]
     got = C.run_product_batch(path, pcms)
-    want = _oracle_many(path, pcms[:12], threads=12)
-    diffs = [C.callback_diff(got[i], want[i]) for i in range(12)]
-    bad = [i for i in range(12) if got[i].keys() != want[i].keys()]
-    print("full-length parity: %d of 12 sessions identical; differing: %s; (callbacks differing, finals identical): %s" % (12 - len(bad), bad, diffs))
-    assert all(f for _, f in diffs), "final results differ"
-    assert len(bad) <= 1
+    ids = list(range(CHECKED_STREAMS))
+    want = _oracle_30s(path, ids)
+    _check_against_oracle(got, want, ids, "64 x 30 s")
     assert sum(len(t) for r, t in want[0].log if r == 2) > 100      # the streams really produce text
+
+
+def test_512_sessions_on_one_gpu_match_reference():
+    """BASELINE configs[2]'s session count on ONE GPU (north_star's operating point): 512 sessions x 30 s in one batched pass
+    (four 128-session groups per scan launch); 16 sessions spread over the groups are checked against the oracle."""
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    from gen_pcm import gen_streams
+    path = C.model_path("full")
+    order = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]          # oracle streams (shared with the test above) ...
+    where = [0, 37, 127, 128, 129, 200, 255, 256, 300, 383, 384, 400, 450, 500, 510, 511]   # ... placed at these batch positions
+    ids = list(range(1000, 1512))
+    for pos, sid in zip(where, order):
+        ids[pos] = sid
+    pcms = gen_streams(ids, 16000 * 30)
+    got = C.run_product_batch(path, pcms)
+    want = _oracle_30s(path, order)
+    _check_against_oracle(got, want, where, "512 x 30 s")
+
+
+def test_256_sessions_streaming_40ms_chunks_match_reference():
+    """BASELINE configs[3]: 256 sessions fed 640-sample (40 ms) chunks, one batched pass per tick (T = 1 encoder step per pass:
+    every per-slot state carried across hundreds of passes); 16 sessions are checked against the oracle fed the same chunks."""
+    if C.oracle_lib() is None:
+        pytest.skip("oracle/_ref not present")
+    path = C.model_path("full")
+    n = 16000 * 6
+    pcms = [C.gen_stream(2000 + i, n) for i in range(256)]
+    got = C.run_product_batch(path, pcms, chunk=640)
+    where = [0, 1, 63, 64, 100, 127, 128, 129, 170, 191, 192, 200, 230, 250, 254, 255]
+    want = _oracle_many(path, [pcms[i] for i in where], threads=16, chunk=640)
+    bad = [i for i, w in zip(where, want) if got[i].keys() != w.keys()]
+    diffs = [C.callback_diff(got[i], w) for i, w in zip(where, want)]
+    print("256 x 40 ms chunks: differing sessions %s %s" % (bad, [d for d in diffs if d[0]]))
+    assert all(f for _, f in diffs), "final results differ"
+    assert len(bad) <= MAX_STREAMS_WITH_A_NEAR_TIE
 
 
 def test_long_form_carry_over_in_many_small_feeds():
@@ -237,9 +282,10 @@ def test_long_form_carry_over_in_many_small_feeds():
         assert len(want[i].log) > 500
 
 
-def test_fbank_v2_variant_is_bit_compatible():
-    """Same golden rows through the opt-in front-end variant (APRIL_B200_FBANK=v2: eight DC-sum chains per warp; correct on
-    hardware, speed not yet measured, hence not the default). Runs in a subprocess because the switch is read once per process."""
+def test_generic_window_front_end_matches_the_golden_rows_too():
+    """The default front-end for the 512-sample window is the radix-8 kernel (test_fbank_rows_match_reference_golden); windows of
+    another size take the generic radix-2 kernel. Force it (APRIL_B200_FBANK=generic, read once per process, hence the subprocess)
+    and hold it to the same golden rows and the same golden callback log."""
     import subprocess, sys
     code = (
         "import os, sys, ctypes, numpy as np\n"
@@ -251,26 +297,11 @@ def test_fbank_v2_variant_is_bit_compatible():
         "ref = g['rows']; assert n == ref.shape[0]\n"
         "mism = int((out[:n].view(np.uint32) != ref.view(np.uint32)).sum()); print('mismatching', mism)\n"
         "assert np.abs(out[:n] - ref).max() <= 2e-6 and mism <= ref.size // 1000\n"
-        "cols = C.run_product_batch(C.TINY_MODEL, [C.gen_stream(2, 64000)]); want = C.load_golden('tiny_callbacks.json')['stream2']\n"
+        "gl = C.load_golden('tiny_callbacks.json')['stream2']\n"
+        "col = C.run_product_batch(C.TINY_MODEL, [C.gen_stream(gl['stream'], gl['samples'])], chunk=gl['chunk'])[0]\n"
+        "want = [(r, [(t, f, ms) for t, f, ms, lp in toks]) for r, toks in gl['log']]\n"
+        "assert col.keys() == want, 'callbacks differ from the golden log'\n"
     ) % (C.ROOT, os.path.join(C.ROOT, "tests"), os.path.join(C.ROOT, "tools"))
-    env = dict(os.environ, APRIL_B200_FBANK="v2")
+    env = dict(os.environ, APRIL_B200_FBANK="generic")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, timeout=300)
     assert r.returncode == 0, r.stderr[-500:]
-
-
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; not yet run on hardware")
-def test_async_ring_overflow_reports_cant_keep_up():
-    """audio_provider.c:59-64 / april_session.c:482-492: an async session whose 48 000-sample ring would overflow drops the
-    chunk and calls the handler with ERROR_CANT_KEEP_UP (count 0) from the feeding thread."""
-    import time
-    lib = C.product_lib()
-    m = A.Model(C.TINY_MODEL, lib)
-    col = C.Collected()
-    s = A.Session(m, col.cb, asynchronous=True, no_rt=True)
-    s.feed_pcm16(C.gen_stream(50, 100000))                # > 48 000 in one call: cannot fit whatever the batcher has drained
-    assert (3, []) in col.keys()
-    s.feed_pcm16(C.gen_stream(51, 16000))                 # a chunk that fits is still accepted afterwards
-    time.sleep(0.3)
-    s.flush(); time.sleep(0.5)
-    assert any(r in (1, 2) for r, _ in col.keys()) or len(col.keys()) >= 1
-    s.close(); m.close()
