@@ -30,7 +30,9 @@ using namespace tc;
 constexpr int UNITS = 8;          // hidden units whose cell update a CTA owns
 constexpr int GROUP = 128;        // sessions per group = UMMA M
 constexpr int MAXG = 4;           // interleaved groups per launch (512 sessions)
-constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter: each takes 4 of the CTA's 8 units
+constexpr int EPI_WARPS = 8;      // warps per epilogue team: two per TMEM lane quarter, each takes 4 of the CTA's 8 units
+constexpr int TEAMS = 2;          // epilogue teams: team k serves groups k, k + 2 (measured on B200 with one team: the TMEM drain,
+                                  // pair exchange and cell update of an item keep a team busy ~5.5 us, longer than the item's MMAs)
 constexpr uint32_t TILE_BYTES = GROUP * 128u;   // [128 sessions x 64 k] fp16, 128B-swizzled
 
 struct Args {
@@ -99,7 +101,8 @@ template <int CS, int MMAW> struct Cfg {
     static constexpr int RST = CS == 2 ? 4 : 3;                 // ring stages (16 KB tiles)
     static constexpr int XBUF = CS == 2 ? 2 : 1;                // exchange block buffers
     static constexpr int NSLOT = (512 / (MMAW * NC)) > 4 ? 4 : (512 / (MMAW * NC));   // accumulator sets in TMEM
-    static constexpr int WARPS = 1 + MMAW + EPI_WARPS + 2;      // producer, MMA issuers, epilogue, two releasers (groups k, k + 2)
+    static constexpr int WARPS = 1 + MMAW + TEAMS * EPI_WARPS + 1;   // producer, MMA issuers, epilogue teams, releaser (20 warps with MMAW = 2: five per
+                                                                     // scheduler, i.e. 96 registers per thread)
     static constexpr int THREADS = WARPS * 32;
     static constexpr uint32_t XSRC_BYTES = 2u * 4u * GROUP * 16u;   // one source rank's block: [hc][16-byte chunk][session] = 16 KB
     static constexpr uint32_t XB_BYTES = (CS - 1) * XSRC_BYTES;
@@ -229,26 +232,30 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                 __syncwarp();
                 if (mw == 0 && lane == 0) TRACE4(3);
             }
-    } else if (warp < 1 + MMAW + EPI_WARPS) {
-        // ===================== epilogue: one thread = one session x 4 of my units (and the same 4-unit column block of every peer) ============
-        const int ew = warp - (1 + MMAW);
+    } else if (warp < 1 + MMAW + TEAMS * EPI_WARPS) {
+        // ===================== epilogue teams: one thread = one session x 4 of my units (and the same 4-unit column block of every peer) =====
+        const int team = (warp - (1 + MMAW)) / EPI_WARPS;
+        const int ew = (warp - (1 + MMAW)) % EPI_WARPS;
         const int q = warp & 3, hc = ew >> 2;                             // TMEM lane quarter this warp may read; which half of a CTA's units
         const int sl = q * 32 + lane;                                     // session lane within the group
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int ucol = u0 + hc * 4;                                     // first of my 4 units
-        float cst[MAXG][4];
-        int nlive[MAXG];
+        constexpr int GPT = MAXG / TEAMS;                                 // groups per team: slot gi serves group gi * TEAMS + team
+        float cst[GPT][4];
+        int nlive[GPT];
 #pragma unroll
-        for (int g = 0; g < MAXG; g++) {
+        for (int gi = 0; gi < GPT; gi++) {
+            const int g = gi * TEAMS + team;
             const bool valid = g < NG && sl < a.Bg[g];
             const int sess = a.g0 + a.goff[g] + sl;
-            nlive[g] = valid ? a.nsteps[sess] : 0;
+            nlive[gi] = valid ? a.nsteps[sess] : 0;
             float4 c4 = valid ? *reinterpret_cast<const float4*>(a.c_state + (size_t)sess * a.H + ucol) : make_float4(0.f, 0.f, 0.f, 0.f);
-            cst[g][0] = c4.x; cst[g][1] = c4.y; cst[g][2] = c4.z; cst[g][3] = c4.w;
+            cst[gi][0] = c4.x; cst[gi][1] = c4.y; cst[gi][2] = c4.z; cst[gi][3] = c4.w;
         }
         for (int t = 0; t < a.T; t++) {
 #pragma unroll
-            for (int g = 0; g < MAXG; g++) {
+            for (int gi = 0; gi < GPT; gi++) {
+                const int g = gi * TEAMS + team;
                 if (g >= NG) break;
                 const uint32_t item = (uint32_t)(t * NG + g);
                 const int slot = (int)(item % NSLOT);
@@ -257,13 +264,6 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                 const bool valid = sl < a.Bg[g];
                 const bool warp_valid = q * 32 < a.Bg[g];
                 const int sess = a.g0 + a.goff[g] + sl;
-                // input gates of my 4 units: issued now, needed after the exchange
-                float4 gin[4];
-                if (valid) {
-                    const float* gp = a.G + ((size_t)t * a.Bs + sess) * 4 * a.H + ucol;
-#pragma unroll
-                    for (int g4 = 0; g4 < 4; g4++) gin[g4] = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)g4 * a.H));
-                }
                 mbar_wait(tfull_bar(slot), (item / NSLOT) & 1);
                 if (ew == 0 && lane == 0) TRACE4(4);
                 tc_fence_after();
@@ -311,6 +311,13 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                     for (int pp = 1; pp < CS; pp++) mbar_arrive_remote(mapa_(prfull_bar(xb), (rank + pp) % CS));
                 }
                 if (ew == 0 && lane == 0) TRACE4(5);
+                // input gates of my 4 units: in flight while the peers' partial sums arrive
+                float4 gin[4];
+                if (valid) {
+                    const float* gp = a.G + ((size_t)t * a.Bs + sess) * 4 * a.H + ucol;
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; g4++) gin[g4] = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)g4 * a.H));
+                }
                 if (CS > 1) {
                     mbar_wait_cluster(prfull_bar(xb), xuse & 1);          // the other K-slices' sums for my units
                     if (valid) {
@@ -331,24 +338,24 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                 }
                 if (ew == 0 && lane == 0) TRACE4(6);
                 if (valid) {
-                    const bool live = a.t0 + t < nlive[g];                // ragged: finished sessions keep their state
-                    const float gi[4] = { gin[0].x, gin[0].y, gin[0].z, gin[0].w }, gf[4] = { gin[1].x, gin[1].y, gin[1].z, gin[1].w },
-                                gg[4] = { gin[2].x, gin[2].y, gin[2].z, gin[2].w }, go[4] = { gin[3].x, gin[3].y, gin[3].z, gin[3].w };
+                    const bool live = a.t0 + t < nlive[gi];                // ragged: finished sessions keep their state
+                    const float xi[4] = { gin[0].x, gin[0].y, gin[0].z, gin[0].w }, xf[4] = { gin[1].x, gin[1].y, gin[1].z, gin[1].w },
+                                xg[4] = { gin[2].x, gin[2].y, gin[2].z, gin[2].w }, xo[4] = { gin[3].x, gin[3].y, gin[3].z, gin[3].w };
                     float mval[4];
                     __align__(8) __half mh[4], ml[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const float pi = mine[u] * a.inv_scale + gi[u], pf = mine[4 + u] * a.inv_scale + gf[u];
-                        const float pg = mine[8 + u] * a.inv_scale + gg[u], po = mine[12 + u] * a.inv_scale + go[u];
-                        const float cn = fast_sigmoid(pf) * cst[g][u] + fast_sigmoid(pi) * fast_tanh(pg);
+                        const float pi = mine[u] * a.inv_scale + xi[u], pf = mine[4 + u] * a.inv_scale + xf[u];
+                        const float pg = mine[8 + u] * a.inv_scale + xg[u], po = mine[12 + u] * a.inv_scale + xo[u];
+                        const float cn = fast_sigmoid(pf) * cst[gi][u] + fast_sigmoid(pi) * fast_tanh(pg);
                         mval[u] = fast_sigmoid(po) * fast_tanh(cn);
-                        if (live) cst[g][u] = cn;
+                        if (live) cst[gi][u] = cn;
                         split_f16(mval[u], mh[u], ml[u]);
                     }
                     const size_t orow = ((size_t)(t + 1) * a.Bs + sess) * a.H + ucol;
                     *reinterpret_cast<uint2*>(a.Mx_hi + orow) = *reinterpret_cast<const uint2*>(mh);
                     *reinterpret_cast<uint2*>(a.Mx_lo + orow) = *reinterpret_cast<const uint2*>(ml);
-                    if (live && ((a.t0 + t == nlive[g] - 1) || (t == a.T - 1)))
+                    if (live && ((a.t0 + t == nlive[gi] - 1) || (t == a.T - 1)))
                         *reinterpret_cast<float4*>(a.m_state + (size_t)sess * a.H + ucol) = make_float4(mval[0], mval[1], mval[2], mval[3]);
                 }
                 __syncwarp();
@@ -356,15 +363,16 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
             }
         }
 #pragma unroll
-        for (int g = 0; g < MAXG; g++)
+        for (int gi = 0; gi < GPT; gi++) {
+            const int g = gi * TEAMS + team;
             if (g < NG && sl < a.Bg[g])
-                *reinterpret_cast<float4*>(a.c_state + (size_t)(a.g0 + a.goff[g] + sl) * a.H + ucol) = make_float4(cst[g][0], cst[g][1], cst[g][2], cst[g][3]);
+                *reinterpret_cast<float4*>(a.c_state + (size_t)(a.g0 + a.goff[g] + sl) * a.H + ucol) = make_float4(cst[gi][0], cst[gi][1], cst[gi][2], cst[gi][3]);
+        }
     } else {
-        // ===================== releasers: the gpu-scope release (store acknowledgement ~1 us) must not hold the epilogue; warp k serves groups k, k + 2 ====
-        const int k = warp - (1 + MMAW + EPI_WARPS);
+        // ===================== releaser: the gpu-scope release (store acknowledgement ~1 us) must not hold an epilogue team ====
         if (lane == 0)
             for (int t = 0; t < a.T; t++)
-                for (int g = k; g < NG; g += 2) {
+                for (int g = 0; g < NG; g++) {
                     mbar_wait(rel_bar(g), t & 1);
                     asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> the other CTAs' TMA (async proxy) reads
                     red_release(a.counter + g * 64);                      // one 256-byte stride per group
