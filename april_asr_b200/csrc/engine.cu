@@ -17,6 +17,7 @@
 #include "kernels_scan2.cuh"
 #include "kernels_scan3.cuh"
 #include "kernels_scan4.cuh"
+#include "kernels_greedy_tc.cuh"
 
 namespace april {
 
@@ -241,6 +242,12 @@ public:
     float* dout_blank = nullptr;
     float* dtab = nullptr;            // decoder output table [V][V][J] (fast greedy path)
     bool fast_greedy = false;
+    // tensor-core joiner + search (kernels_greedy_tc.cuh): joiner rows as fp16 (hi, lo) per cluster rank
+    bool greedy_tc = false;
+    __half* gt_w = nullptr;
+    float gt_inv = 1.f;
+    CUtensorMap gt_mapW;
+    size_t gt_smem = 0;
     int gr_R = 0;
     size_t gr_smem = 0;
     int frame_N = 0, frame_shift = 0;
@@ -428,6 +435,30 @@ public:
         CK(cudaFree(Y));
         CK(cudaFuncSetAttribute(k::greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gr_smem));
         fast_greedy = true;
+        init_greedy_tc();
+    }
+
+    // the tensor-core search needs the decoder table (above), V <= 8 x 64 vocabulary rows and J in whole 64-wide k-blocks
+    void init_greedy_tc() {
+        const int V = d.V, J = d.J;
+        const char* sel = getenv("APRIL_B200_GREEDY");
+        if (npass == 0 || !(sel && !strcmp(sel, "tc")) || V > gt::CLUSTER * gt::RV || J % 64 != 0 || J > 512) return;   // opt-in until validated on hardware
+        gt_smem = gt::smem_bytes(J, V);
+        if (gt_smem > 227 * 1024) return;
+        if (cudaFuncSetAttribute(gt::joiner_greedy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem) != cudaSuccess) { cudaGetLastError(); return; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(gt::CLUSTER); cfg.blockDim = dim3(gt::THREADS); cfg.dynamicSmemBytes = gt_smem; cfg.stream = st;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, gt::joiner_greedy_tc_kernel, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return; }
+        std::vector<float> jw((size_t)V * J);
+        CK(cudaMemcpy(jw.data(), jp.join_w, sizeof(float) * jw.size(), cudaMemcpyDeviceToHost));
+        const float sc = pow2_scale(jw, gt_inv);
+        CK(cudaMalloc(&gt_w, sizeof(__half) * (size_t)gt::CLUSTER * 2 * gt::RV * J)); owned.push_back(gt_w);
+        gt::pack_joiner_kernel<<<dim3(gt::CLUSTER, gt::RV), 128, 0, st>>>(jp.join_w, gt_w, V, J, sc);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        gt_mapW = make_map_2d(gt_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)gt::CLUSTER * 2 * gt::RV, (uint64_t)J, 64, gt::RV, true);
+        greedy_tc = true;
     }
 
     size_t conv_smem() const {
@@ -1201,7 +1232,16 @@ public:
                 else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
                 span_begin(2);
-                if (fast_greedy) {
+                if (greedy_tc) {
+                    const int maxc = std::max(1, num_sms / gt::CLUSTER);
+                    gt::Args ga{};
+                    ga.J = J; ga.V = d.V; ga.blank = prm.blank_id; ga.B = B; ga.Tcap = Tmax; ga.t_base = t0; ga.chunk_T = tc; ga.stride_ms = stride_ms(); ga.last_chunk = last;
+                    ga.S = std::min(gt::MAX_S, std::max(1, (B + maxc - 1) / maxc));
+                    ga.inv_scale = gt_inv; ga.bias = jp.join_b; ga.vflags = jp.vflags; ga.dtab = dtab; ga.enc_out = EO; ga.nsteps = d_nsteps; ga.slot = d_slot; ga.flush_flag = d_flush;
+                    ga.gstate = gstate; ga.rec = b_rec.as<k::DecisionRecord>(); ga.npass = b_np.as<int>(); ga.tap_logits = want_tap ? b_tap.as<float>() : nullptr;
+                    const int ncl = (B + ga.S - 1) / ga.S;
+                    gt::joiner_greedy_tc_kernel<<<ncl * gt::CLUSTER, gt::THREADS, gt_smem, st>>>(gt_mapW, ga);
+                } else if (fast_greedy) {
                     const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
                     const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));
                     const int ncl = (B + S - 1) / S;

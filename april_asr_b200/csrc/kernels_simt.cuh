@@ -102,6 +102,7 @@ fbank_kernel(FbankParams P, const int16_t* __restrict__ pcm, const long long* __
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             int j = base + u * 32 + lane;
+            if (j >= N) { cur[u] = prev[u] = 0.0; continue; }            // windows shorter than 256 samples (N = 64, 128)
             cur[u] = __dsub_rn(dat[j], dmean);
             prev[u] = __dsub_rn(dat[j > 0 ? j - 1 : 0], dmean);
         }
@@ -109,6 +110,7 @@ fbank_kernel(FbankParams P, const int16_t* __restrict__ pcm, const long long* __
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             int j = base + u * 32 + lane;
+            if (j >= N) continue;
             double v = __dsub_rn(cur[u], __dmul_rn(coeff, prev[u]));
             v = __dmul_rn(v, (double)P.window[j]);   // fbank.c:256-257
             int rj = __brev((unsigned)j) >> (32 - P.log2N);
