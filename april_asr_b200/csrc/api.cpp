@@ -153,10 +153,20 @@ static void sync_submit(AprilASRSession_i* s, const int16_t* pcm, size_t count, 
     while (!r.done) {
         if (L.leader_active) { L.qcv.wait(lk); continue; }
         L.leader_active = true;                              // I lead: my request is in the queue, so it is part of my batch
+        // Coalescing window: wait while callers keep arriving — until every live synchronous session of this GPU has a call queued,
+        // or nobody new came for `win` microseconds, or 20 windows have passed. 256 threads released by the same 40 ms audio tick
+        // arrive over a few hundred microseconds; a lone caller among many idle sessions pays one window.
         const long win = L.model->coalesce_us;
         if (win > 0 && (int)L.queue.size() < L.live_sync && L.miss_streak < 4) {
-            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(win);
-            while ((int)L.queue.size() < L.live_sync && L.qcv.wait_until(lk, deadline) != std::cv_status::timeout) {}
+            const auto cap = std::chrono::steady_clock::now() + std::chrono::microseconds(20 * win);
+            for (;;) {
+                const size_t seen = L.queue.size();
+                if ((int)seen >= L.live_sync) break;
+                const auto now = std::chrono::steady_clock::now();
+                if (now >= cap) break;
+                L.qcv.wait_until(lk, std::min(cap, now + std::chrono::microseconds(win)));
+                if (L.queue.size() == seen && std::chrono::steady_clock::now() >= now + std::chrono::microseconds(win)) break;   // a quiet window
+            }
         }
         std::vector<SyncReq*> batch;
         batch.swap(L.queue);

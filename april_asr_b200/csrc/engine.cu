@@ -747,12 +747,8 @@ public:
         if (sel && strcmp(sel, "v4")) return;                              // an older kernel was asked for
         if (H % 128 || H / scan4::UNITS > num_sms || D % 8) return;     // K slices are whole 64-wide k-blocks
         const int GC = H / scan4::UNITS;
-        if (const char* e = getenv("APRIL_B200_SCAN_CS")) scan4_cs = atoi(e);
-        if (const char* e = getenv("APRIL_B200_SCAN_MMAW")) scan4_mmaw = atoi(e);
-        if (H % 256) scan4_cs = 2;
-        bool ok = false;
-        if (scan4_cs == 4) { scan4_mmaw = 2; ok = scan4_prepare_variant<4, 2>(GC); }
-        if (!ok) { scan4_cs = 2; if (scan4_mmaw != 4) scan4_mmaw = 2; ok = scan4_mmaw == 4 ? scan4_prepare_variant<2, 4>(GC) : scan4_prepare_variant<2, 2>(GC); }
+        scan4_cs = 2; scan4_mmaw = 2;
+        const bool ok = scan4_prepare_variant<2, 2>(GC);
         if (!ok) return;
         const int CS = scan4_cs, NC = 32 * CS, Kc = H / CS;
         float *dA = nullptr, *dB = nullptr, *dC = nullptr;
@@ -793,9 +789,9 @@ public:
             const int Bc = std::min(per_launch, B - g0);
             scan4::Args a{};
             a.T = tc; a.t0 = t0;
-            // two epilogue teams (groups k, k + 2): an even number of groups keeps both busy; a group costs a full M = 128 set of MMAs
-            // whatever its size, so small batches are not split further
-            a.NG = Bc > 2 * scan4::GROUP ? 4 : (Bc >= 16 ? 2 : 1);
+            // a group costs a full M = 128 set of MMAs whatever its size and every group walks the same dependent chain, so a batch is
+            // split only when it does not fit one group
+            a.NG = (Bc + scan4::GROUP - 1) / scan4::GROUP;
             if (groups_env >= (Bc + scan4::GROUP - 1) / scan4::GROUP && groups_env <= scan4::MAXG && Bc >= 8 * groups_env) a.NG = groups_env;
             const int per = ((Bc + a.NG - 1) / a.NG + 7) & ~7;
             for (int g = 0, o = 0; g < scan4::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::max(0, std::min(per, Bc - o)) : 0; o += a.Bg[g]; }
@@ -808,9 +804,7 @@ public:
             if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
             CK(cudaMemsetAsync(scan_counters, 0, 256 * sizeof(unsigned), st));
             const CUtensorMap mh = make_map_f16(Mh, (uint64_t)(tc + 1) * B, (uint64_t)H, (uint32_t)a.Bp), ml = make_map_f16(Ml, (uint64_t)(tc + 1) * B, (uint64_t)H, (uint32_t)a.Bp);
-            if (scan4_cs == 4) scan4_launch<4, 2>(sl, mh, ml, a);
-            else if (scan4_mmaw == 4) scan4_launch<2, 4>(sl, mh, ml, a);
-            else scan4_launch<2, 2>(sl, mh, ml, a);
+            scan4_launch<2, 2>(sl, mh, ml, a);
             launch_check();
             if (do_trace) dump_trace(a.GC, tc, 1);
         }

@@ -41,17 +41,10 @@ def main():
     a = ap.parse_args()
     if a.child:
         return child(a)
-    import threading
     import numpy as np
     import common as C
     path = C.model_path(a.model)
     pcms = [C.gen_stream(900 + i, int(16000 * a.seconds)) for i in range(a.streams)]
-    want = [None] * a.streams
-
-    def work(i):
-        want[i] = C.run_oracle(path, pcms[i], tap=True)
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(a.streams)]
-    for t in ts: t.start()
     report = {"model": a.model, "streams": a.streams, "seconds": a.seconds, "configs": []}
     runs = []
     for name, envs in CONFIGS:
@@ -63,7 +56,7 @@ def main():
                            env=env, capture_output=True, text=True, timeout=1200)
         runs.append((name, envs, dict(np.load(f)) if r.returncode == 0 else None, r.stderr[-400:]))
         if r.returncode == 0: os.unlink(f)
-    for t in ts: t.join()
+    want = [C.run_oracle(path, p, tap=True) for p in pcms]       # one after the other: the oracle's tap is a process-wide hook
     for name, envs, got, err in runs:
         if got is None:
             report["configs"].append({"name": name, "env": envs, "failed": err}); continue

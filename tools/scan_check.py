@@ -19,6 +19,7 @@ def child(a):
     out = {}
     for i, c in enumerate(cols):
         out["enc%d" % i] = np.stack(c.enc) if c.enc else np.zeros((0, 1), np.float32)
+        out["lg%d" % i] = np.stack(c.logits) if c.logits else np.zeros((0, 1), np.float32)
         out["keys%d" % i] = np.array(json.dumps(c.keys()))
     np.savez(a.child, **out)
 
@@ -54,8 +55,13 @@ def main():
         if err: print("\n".join(err[:12]))
         res[arm] = dict(np.load(f)); os.unlink(f)
     if res["a"] is not None and res["b"] is not None:
-        worst = 0.0; nkeys = 0
+        worst = 0.0; nkeys = 0; worst_lg = 0.0
         for i in range(a.sessions):
+            la, lb = res["a"]["lg%d" % i], res["b"]["lg%d" % i]
+            if la.shape == lb.shape and la.size:
+                worst_lg = max(worst_lg, float(np.abs(la - lb).max()))
+            elif la.shape != lb.shape:
+                print("session %d: logit shapes differ %s %s" % (i, la.shape, lb.shape))
             ea, eb = res["a"]["enc%d" % i], res["b"]["enc%d" % i]
             if ea.shape != eb.shape:
                 print("session %d: shapes differ %s %s" % (i, ea.shape, eb.shape)); continue
@@ -67,7 +73,7 @@ def main():
                     first = int(np.argmax(per_step > 1e-3))
                     print("session %d: max |a-b| %.3g, first step above 1e-3: %d of %d, nan a/b: %d/%d" % (i, d.max(), first, len(per_step), int(np.isnan(ea).sum()), int(np.isnan(eb).sum())))
             nkeys += int(str(res["a"]["keys%d" % i]) == str(res["b"]["keys%d" % i]))
-        print("A=[%s] vs B=[%s] model=%s sessions=%d: max |enc_a - enc_b| = %.3g; identical callback logs: %d of %d" % (a.a, a.b, a.model, a.sessions, worst, nkeys, a.sessions))
+        print("A=[%s] vs B=[%s] model=%s sessions=%d: max |enc_a - enc_b| = %.3g, max |logits_a - logits_b| = %.3g; identical callback logs: %d of %d" % (a.a, a.b, a.model, a.sessions, worst, worst_lg, nkeys, a.sessions))
     if a.oracle and res["b"] is not None:
         import common as C
         path = C.model_path(a.model)
