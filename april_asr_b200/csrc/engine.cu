@@ -4,6 +4,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -21,10 +22,16 @@
 
 namespace april {
 
+// CUDA errors abort the process (the reference's ORT_ABORT_ON_ERROR policy, src/ort_util.h:29-38) — except while a small pass is being
+// captured into a CUDA graph: there a failure only cancels the capture and the pass runs eagerly.
+static thread_local bool tl_soft_errors = false, tl_soft_failed = false;
+static std::atomic<uint64_t> g_buf_gen{ 0 };       // bumped whenever a device / pinned work buffer is reallocated: cached graphs hold their addresses
+
 #define CK(x)                                                                                              \
     do {                                                                                                   \
         cudaError_t e_ = (x);                                                                              \
         if (e_ != cudaSuccess) {                                                                           \
+            if (tl_soft_errors) { tl_soft_failed = true; break; }                                          \
             fprintf(stderr, "libapril: (engine) [ERROR] CUDA: %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
             abort();                                                                                       \
         }                                                                                                  \
@@ -141,6 +148,7 @@ struct DevBuf {
         size_t want = bytes + bytes / 8 + 256;
         CK(cudaMalloc(&p, want));
         cap = want;
+        g_buf_gen++;
     }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
     ~DevBuf() { if (p) cudaFree(p); }
@@ -155,6 +163,7 @@ struct PinBuf {
         size_t want = bytes + bytes / 4 + 4096;
         CK(cudaMallocHost(&p, want));
         cap = want;
+        g_buf_gen++;
     }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
     ~PinBuf() { if (p) cudaFreeHost(p); }
@@ -251,6 +260,17 @@ public:
     int gr_R = 0;
     size_t gr_smem = 0;
     int frame_N = 0, frame_shift = 0;
+
+    // CUDA graphs of small passes (streaming: every tick enqueues the same ~110 launches with the same geometry; launching them one by
+    // one is CPU-bound at ~3 ms per pass). Key = everything the enqueue depends on besides device-resident per-session integers.
+    struct GraphKey {
+        int B = -1, Tmax = 0, max_new = 0, row_pitch = 0, any_flush = 0; size_t pcm_total = 0; uint64_t gen = 0;
+        bool operator==(const GraphKey& o) const { return B == o.B && Tmax == o.Tmax && max_new == o.max_new && row_pitch == o.row_pitch && any_flush == o.any_flush && pcm_total == o.pcm_total && gen == o.gen; }
+    };
+    struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; uint64_t launches = 0, h2d = 0, d2h = 0; size_t rec_bytes = 0, np_bytes = 0; };
+    std::vector<CachedGraph> graphs;      // a few most recent
+    GraphKey pending_key;                 // geometry of the previous eager small pass: captured when it repeats
+    bool graphs_ok = true, capturing = false;
 
     // per-slot state
     int slot_cap = 0;
@@ -468,6 +488,7 @@ public:
     ~EngineImpl() override {
         cudaSetDevice(dev);
         if (st) cudaStreamSynchronize(st);
+        for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
         for (void* p : owned) cudaFree(p);
         cudaFree(dout_blank); cudaFree(dtab); cudaFree(m_store); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
         if (st) cudaStreamDestroy(st);
@@ -737,7 +758,7 @@ public:
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 2;
+        cfg.attrs = at; cfg.numAttrs = capturing ? 1 : 2;          // graph capture: plain launch (co-residency was checked at init: 1 CTA per SM, grid <= SMs)
         CK(cudaLaunchKernelEx(&cfg, scan4::lstm_scan4_kernel<CS, MW>, sl.mapW, mh, ml, a));
     }
 
@@ -1084,12 +1105,6 @@ public:
         } else {
             for (int b = 0; b < B; b++) stage_one(b);
         }
-        cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
-        CK(cudaEventRecord(ev0, st));
-        b_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
-        if (pcm_total) CK(cudaMemcpyAsync(b_pcm.p, hp, pcm_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        stat.h2d_bytes += pcm_total * sizeof(int16_t);
-
         // per-session ints as struct-of-arrays
         const size_t nI = (size_t)B;
         const size_t meta_bytes = (9 * nI + (nI & 1)) * sizeof(int) + nI * sizeof(long long);
@@ -1103,6 +1118,17 @@ public:
             h_slot[b] = m.slot; h_carry[b] = m.carry; h_nnew[b] = m.n_new; h_padb[b] = m.pad_before; h_nfr[b] = m.n_frames; h_nsteps[b] = m.nsteps;
             h_flush[b] = m.flush_flag; h_keepf[b] = m.keep_first; h_nkeep[b] = m.n_keep; h_off[b] = m.pcm_off;
         }
+        cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
+        size_t rec_bytes = 0, np_bytes = 0;
+        const bool want_tap = tap != nullptr;
+        bool any_flush_k = false;
+        for (int b = 0; b < B; b++) any_flush_k |= items[(size_t)b].flush;
+        // everything from the uploads to the result copies is enqueued by this lambda: eagerly, or once into a CUDA graph
+        auto enqueue = [&](bool eager) {
+        b_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
+        if (pcm_total) CK(cudaMemcpyAsync(b_pcm.p, hp, pcm_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        stat.h2d_bytes += pcm_total * sizeof(int16_t);
+
         b_meta.ensure(meta_bytes);
         CK(cudaMemcpyAsync(b_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
         stat.h2d_bytes += meta_bytes;
@@ -1111,7 +1137,7 @@ public:
             *d_flush = dm + 6 * nI, *d_keepf = dm + 7 * nI, *d_nkeep = dm + 8 * nI;
         long long* d_off = reinterpret_cast<long long*>(dm + 9 * nI + (nI & 1));
 
-        CK(cudaEventRecord(evc, st));     // uploads done: what follows is the device-resident part of the pass
+        if (eager) CK(cudaEventRecord(evc, st));     // uploads done: what follows is the device-resident part of the pass
         // ---- front-end ------------------------------------------------------------------------------
         b_fb.ensure(sizeof(float) * (size_t)B * row_pitch * MEL);
         float* FB = b_fb.as<float>();
@@ -1130,8 +1156,6 @@ public:
         span_end();
 
         // ---- encoder + search, in time chunks -------------------------------------------------------
-        size_t rec_bytes = 0, np_bytes = 0;
-        const bool want_tap = tap != nullptr;
         if (Tmax > 0) {
             const size_t row_budget = 160 * 1024;                                  // rows per chunk (bounds the activations to a few GB)
             int Tc = (int)std::max<size_t>(1, std::min<size_t>((size_t)Tmax, row_budget / (size_t)B));
@@ -1270,12 +1294,50 @@ public:
             }
         }
         k::carry_out_kernel<<<B, 128, 0, st>>>(carry_store, d_slot, d_keepf, d_nkeep, FB, row_pitch, MEL, CARRY_CAP); launch_check();
+        };
+        // small passes with a geometry seen before replay a graph; the second occurrence of a geometry captures it
+        static const bool graphs_env = !(getenv("APRIL_B200_GRAPHS") && !strcmp(getenv("APRIL_B200_GRAPHS"), "0"));
+        const bool small = graphs_ok && graphs_env && !profile && !want_tap && Tmax <= 8 && (size_t)B * (size_t)std::max(Tmax, 1) <= 8192;
+        GraphKey key; key.B = B; key.Tmax = Tmax; key.max_new = max_new; key.row_pitch = row_pitch; key.any_flush = any_flush_k ? 1 : 0; key.pcm_total = pcm_total; key.gen = g_buf_gen.load();
+        CachedGraph* hit = nullptr;
+        if (small) for (auto& g : graphs) if (g.key == key) { hit = &g; break; }
+        bool timed_compute = false;
+        CK(cudaEventRecord(ev0, st));
+        if (hit) {
+            CK(cudaGraphLaunch(hit->exec, st));
+            stat.kernel_launches += hit->launches; stat.h2d_bytes += hit->h2d; stat.d2h_bytes += hit->d2h; rec_bytes = hit->rec_bytes; np_bytes = hit->np_bytes;
+        } else if (small && pending_key == key) {
+            const uint64_t l0 = stat.kernel_launches, h0 = stat.h2d_bytes, d0 = stat.d2h_bytes;
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            tl_soft_errors = true; tl_soft_failed = false; capturing = true;
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) { enqueue(false); ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && !tl_soft_failed && graph != nullptr; }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            tl_soft_errors = false; capturing = false;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok && key.gen == g_buf_gen.load()) {
+                CachedGraph g; g.key = key; g.exec = exec; g.launches = stat.kernel_launches - l0; g.h2d = stat.h2d_bytes - h0; g.d2h = stat.d2h_bytes - d0; g.rec_bytes = rec_bytes; g.np_bytes = np_bytes;
+                if (graphs.size() >= 4) { cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
+                graphs.push_back(g);
+                CK(cudaGraphLaunch(exec, st));
+            } else {
+                cudaGetLastError();
+                if (exec) cudaGraphExecDestroy(exec);
+                if (!ok) { graphs_ok = false; fprintf(stderr, "libapril: (engine) [WARNING] CUDA graph capture of small passes is not available; launching eagerly\n"); }
+                stat.kernel_launches = l0; stat.h2d_bytes = h0; stat.d2h_bytes = d0;
+                enqueue(true); timed_compute = true;
+            }
+        } else {
+            enqueue(true); timed_compute = true;
+            pending_key = key; pending_key.gen = g_buf_gen.load();      // buffers may have grown during this eager pass
+            if (!small) pending_key.B = -1;
+        }
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stat.device_ms += ms;
-        CK(cudaEventElapsedTime(&ms, evc, ev1));
+        if (timed_compute) CK(cudaEventElapsedTime(&ms, evc, ev1));
         stat.compute_ms += ms;
         ev_pool.push_back(ev0); ev_pool.push_back(ev1); ev_pool.push_back(evc);
         spans_collect();
