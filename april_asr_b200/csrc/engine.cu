@@ -1097,11 +1097,33 @@ public:
             if (consumed > n_buf) consumed = n_buf;
             fr.tail.assign(dst + consumed, dst + n_buf);
         };
-        const int n_stage = (pcm_total * sizeof(int16_t) >= ((size_t)8 << 20)) ? std::min(B, 8) : 1;   // big passes: the copy into pinned memory is the host's largest cost
+        // Big passes: the copy into pinned memory is the host's largest cost and the H2D transfer the next one. Worker threads stage
+        // the sessions in index order; as soon as a block of sessions is staged its bytes are handed to the copy engine, so the
+        // transfer of block k runs under the staging of block k + 1 (the pass then waits only for the last block's transfer).
+        cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
+        bool pcm_uploaded = false;
+        const int n_stage = (pcm_total * sizeof(int16_t) >= ((size_t)8 << 20)) ? std::min(B, 8) : 1;
         if (n_stage > 1) {
+            b_pcm.ensure(pcm_total * sizeof(int16_t));
+            CK(cudaEventRecord(ev0, st));
+            const int nblk = std::min(B, 8);
+            std::vector<int> blk_end((size_t)nblk);
+            for (int g = 0; g < nblk; g++) blk_end[(size_t)g] = (int)(((long long)B * (g + 1)) / nblk);
+            std::vector<std::atomic<int>> blk_done((size_t)nblk);
+            for (auto& x : blk_done) x.store(0);
+            std::atomic<int> next{ 0 };
+            auto block_of = [&](int b) { int g = 0; while (b >= blk_end[(size_t)g]) g++; return g; };
             std::vector<std::thread> th;
-            for (int k = 0; k < n_stage; k++) th.emplace_back([&, k] { for (int b = k; b < B; b += n_stage) stage_one(b); });   // sessions are disjoint
+            for (int k = 0; k < n_stage; k++) th.emplace_back([&] { for (int b; (b = next.fetch_add(1)) < B;) { stage_one(b); blk_done[(size_t)block_of(b)].fetch_add(1, std::memory_order_release); } });
+            for (int g = 0, b0 = 0; g < nblk; b0 = blk_end[(size_t)g], g++) {
+                const int want = blk_end[(size_t)g] - b0;
+                while (blk_done[(size_t)g].load(std::memory_order_acquire) < want) std::this_thread::yield();
+                const size_t o0 = (size_t)meta[(size_t)b0].pcm_off, o1 = blk_end[(size_t)g] < B ? (size_t)meta[(size_t)blk_end[(size_t)g]].pcm_off : pcm_total;
+                if (o1 > o0) CK(cudaMemcpyAsync(b_pcm.as<int16_t>() + o0, hp + o0, (o1 - o0) * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+            }
             for (auto& t : th) t.join();
+            stat.h2d_bytes += pcm_total * sizeof(int16_t);
+            pcm_uploaded = true;
         } else {
             for (int b = 0; b < B; b++) stage_one(b);
         }
@@ -1118,16 +1140,17 @@ public:
             h_slot[b] = m.slot; h_carry[b] = m.carry; h_nnew[b] = m.n_new; h_padb[b] = m.pad_before; h_nfr[b] = m.n_frames; h_nsteps[b] = m.nsteps;
             h_flush[b] = m.flush_flag; h_keepf[b] = m.keep_first; h_nkeep[b] = m.n_keep; h_off[b] = m.pcm_off;
         }
-        cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
         size_t rec_bytes = 0, np_bytes = 0;
         const bool want_tap = tap != nullptr;
         bool any_flush_k = false;
         for (int b = 0; b < B; b++) any_flush_k |= items[(size_t)b].flush;
         // everything from the uploads to the result copies is enqueued by this lambda: eagerly, or once into a CUDA graph
         auto enqueue = [&](bool eager) {
-        b_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
-        if (pcm_total) CK(cudaMemcpyAsync(b_pcm.p, hp, pcm_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        stat.h2d_bytes += pcm_total * sizeof(int16_t);
+        if (!pcm_uploaded) {
+            b_pcm.ensure(std::max<size_t>(pcm_total, 8) * sizeof(int16_t));
+            if (pcm_total) CK(cudaMemcpyAsync(b_pcm.p, hp, pcm_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+            stat.h2d_bytes += pcm_total * sizeof(int16_t);
+        }
 
         b_meta.ensure(meta_bytes);
         CK(cudaMemcpyAsync(b_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
@@ -1302,7 +1325,7 @@ public:
         CachedGraph* hit = nullptr;
         if (small) for (auto& g : graphs) if (g.key == key) { hit = &g; break; }
         bool timed_compute = false;
-        CK(cudaEventRecord(ev0, st));
+        if (!pcm_uploaded) CK(cudaEventRecord(ev0, st));
         if (hit) {
             CK(cudaGraphLaunch(hit->exec, st));
             stat.kernel_launches += hit->launches; stat.h2d_bytes += hit->h2d; stat.d2h_bytes += hit->d2h; rec_bytes = hit->rec_bytes; np_bytes = hit->np_bytes;
