@@ -14,9 +14,6 @@
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
-#include "kernels_scan.cuh"
-#include "kernels_scan2.cuh"
-#include "kernels_scan3.cuh"
 #include "kernels_scan4.cuh"
 #include "kernels_greedy_tc.cuh"
 
@@ -76,60 +73,6 @@ static CUtensorMap make_map_2d(const void* ptr, CUtensorMapDataType dt, size_t e
     CUresult r = get_encode_tiled()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled failed: %d\n", (int)r); abort(); }
-    return m;
-}
-
-// 3-D view of a row-major fp16 matrix [rows, cols]: {64-wide k-block element, row, k-block index}; one box = box_kb k-blocks of
-// box_rows rows, each k-block landing as a [box_rows x 128 B] 128B-swizzled tile (what UMMA K-major descriptors expect)
-static CUtensorMap make_map_kblocks(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_kb) {
-    CUtensorMap m;
-    cuuint64_t dims[3] = { 64, rows, cols / 64 };
-    cuuint64_t strides[2] = { cols * sizeof(__half), 64 * sizeof(__half) };
-    cuuint32_t box[3] = { 64, box_rows, box_kb };
-    cuuint32_t estr[3] = { 1, 1, 1 };
-    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (3-D) failed: %d\n", (int)r); abort(); }
-    return m;
-}
-
-// 4-D view of a stacked exchange buffer [2 (hi|lo)][rows][cols] fp16: {64-wide k-block element, row, hi|lo, k-block index}; one box =
-// box_kb k-blocks, each landing as a [2 * box_rows x 128 B] 128B-swizzled tile = UMMA B operand with N = 2 * box_rows
-static CUtensorMap make_map_kblocks_hl(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_kb) {
-    CUtensorMap m;
-    cuuint64_t dims[4] = { 64, rows, 2, cols / 64 };
-    cuuint64_t strides[3] = { cols * sizeof(__half), rows * cols * sizeof(__half), 64 * sizeof(__half) };
-    cuuint32_t box[4] = { 64, box_rows, 2, box_kb };
-    cuuint32_t estr[4] = { 1, 1, 1, 1 };
-    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (4-D) failed: %d\n", (int)r); abort(); }
-    return m;
-}
-
-// 3-D view of the gate pre-activations G [rows, 4H] fp32: {unit, gate, row}; one box = 8 units x 4 gates x box_rows rows
-static CUtensorMap make_map_g3(const void* ptr, uint64_t rows, uint64_t H, uint32_t box_units, uint32_t box_rows) {
-    CUtensorMap m;
-    cuuint64_t dims[3] = { H, 4, rows };
-    cuuint64_t strides[2] = { H * sizeof(float), 4 * H * sizeof(float) };
-    cuuint32_t box[3] = { box_units, 4, box_rows };
-    cuuint32_t estr[3] = { 1, 1, 1 };
-    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (G 3-D) failed: %d\n", (int)r); abort(); }
-    return m;
-}
-
-// 5-D view of the scan2 exchange buffer Mx[t][hl][session][H]: {64-wide k-block element, session, hi|lo, k-block, time}
-static CUtensorMap make_map_mx(const void* ptr, uint64_t Bs, uint64_t H, uint64_t Trows, uint32_t box_sessions, uint32_t box_kb) {
-    CUtensorMap m;
-    cuuint64_t dims[5] = { 64, Bs, 2, H / 64, Trows };
-    cuuint64_t strides[4] = { H * sizeof(__half), Bs * H * sizeof(__half), 64 * sizeof(__half), 2 * Bs * H * sizeof(__half) };
-    cuuint32_t box[5] = { 64, box_sessions, 2, box_kb, 1 };
-    cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
-    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (5-D) failed: %d\n", (int)r); abort(); }
     return m;
 }
 
@@ -218,19 +161,7 @@ public:
     DevBuf b_a3_h, b_a3_l;
     struct TcLayer { TcWeight w_ih, ff1, ff2; };
     std::vector<TcLayer> tlayers;
-    // persistent tensor-core scan: stacked (hi;lo) recurrent weights per layer + exchange buffers
-    struct ScanLayer { __half *wg = nullptr, *wp = nullptr; float inv_hh = 1.f, inv_hr = 1.f; CUtensorMap mapWg, mapWp; };
-    std::vector<ScanLayer> slayers;
-    bool scan_tc = false;
-    // single-exchange scan (kernels_scan2.cuh): W_eff = W_hh W_hr slices + W_hr for the layer-output GEMM; recurrent state is m
-    struct Scan2Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; };
-    std::vector<Scan2Layer> s2layers;
-    bool scan2 = false;
-    size_t scan2_smem = 0;
-    int scan2_cs = 1;               // thread-block cluster size of the scan (TMA multicast factor)
     bool gemm_attr[16] = {};
-    bool scan3 = false;             // K split over CTA pairs (kernels_scan3.cuh): same buffers and state as scan2, different W slicing
-    size_t scan3_smem = 0;
     // wide-batch scan (kernels_scan4.cuh): sessions on the UMMA M dimension, K split over clusters of scan4_cs CTAs
     struct Scan4Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; };
     std::vector<Scan4Layer> s4layers;
@@ -238,11 +169,8 @@ public:
     int scan4_cs = 2, scan4_mmaw = 2;
     size_t scan4_smem = 0;
     float* m_store = nullptr;       // [slot][L][H]
-    DevBuf b_mx, b_mall_h, b_mall_l, b_mw;
-    __half *sx_h_hi = nullptr, *sx_h_lo = nullptr, *sx_m_hi = nullptr, *sx_m_lo = nullptr;
+    DevBuf b_mall_h, b_mall_l, b_mw;
     unsigned* scan_counters = nullptr;
-    size_t scan_smem = 0;
-    int scan_kbg = 1;
     DevBuf b_trace;
     DevBuf b_xe_h, b_xe_l, b_x_h, b_x_l, b_x1_h, b_x1_l, b_f1_h, b_f1_l;
     k::JoinerParams jp{};
@@ -328,7 +256,7 @@ public:
             tw_out = make_tc_weight(w.out_w, d.D, d.C3 * d.F3);
             tw_proj = make_tc_weight(w.enc_proj_w, d.J, d.D);
             // conv3 and the subsampler's linear as GEMMs (kernels_tc.cuh: conv12_im2col_kernel)
-            conv_tc = (d.C2 % 8 == 0) && ((d.C2 * 9) % 8 == 0) && (d.C3 % 8 == 0) && ((d.SEG - 2 - 3) / 2 + 1 == 3) && getenv("APRIL_B200_SIMT_CONV") == nullptr;
+            conv_tc = (d.C2 % 8 == 0) && ((d.C2 * 9) % 8 == 0) && (d.C3 % 8 == 0) && ((d.SEG - 2 - 3) / 2 + 1 == 3);
             if (conv_tc) {
                 tw_conv3 = make_tc_weight(w.conv3_w, d.C3, d.C2 * 9);                    // [oc][ic*9 + ky*3 + kx]
                 std::vector<float> perm((size_t)d.D * d.C3 * d.F3);
@@ -347,12 +275,8 @@ public:
                 tl.ff2 = make_tc_weight(lw.ff2_w, d.D, d.F);
                 tlayers.push_back(tl);
             }
-            set_gemm_attrs();
             const char* scan_sel = getenv("APRIL_B200_SCAN");
-            if (!(scan_sel && !strcmp(scan_sel, "simt"))) {          // "simt": per-step fp32 recurrence inside the tensor-core tier (precision studies)
-                init_scan4(w);
-                if (!scan4) { init_scan(w); init_scan2(w); }
-            }
+            if (!(scan_sel && !strcmp(scan_sel, "simt"))) init_scan4(w);   // "simt": per-step fp32 recurrence inside the tensor-core tier (precision studies, tests)
         }
 
         // vocabulary flags (april_session.c:338-351)
@@ -443,7 +367,7 @@ public:
         gr_R = (V + k::GC_CLUSTER - 1) / k::GC_CLUSTER;
         gr_smem = sizeof(float) * ((size_t)4 * k::GC_MAX_S * J + (size_t)k::GC_MAX_S * ((gr_R + 3) & ~3)) + sizeof(k::GreedyPartial) * 2 * k::GC_CLUSTER * k::GC_MAX_S + (size_t)V + 64;
         const size_t tab_bytes = sizeof(float) * (size_t)V * V * J;
-        if (J % 32 != 0 || J / 32 > k::GC_MAX_JPL || J > 512 || gr_R > 8 * k::GC_RPW || gr_smem > 200 * 1024 || tab_bytes > ((size_t)3 << 30) || getenv("APRIL_B200_SLOW_GREEDY")) return;
+        if (J % 32 != 0 || J / 32 > k::GC_MAX_JPL || J > 512 || gr_R > 8 * k::GC_RPW || gr_smem > 200 * 1024 || tab_bytes > ((size_t)3 << 30)) return;
         CK(cudaMalloc(&dtab, tab_bytes));
         float* Y = nullptr;
         CK(cudaMalloc(&Y, sizeof(float) * (size_t)V * d.E));
@@ -568,14 +492,6 @@ public:
         return t;
     }
 
-    static void stack_hi_lo(const std::vector<float>& rows_src, size_t K, float sc, __half* dst_hi, __half* dst_lo) {
-        for (size_t i = 0; i < rows_src.size(); i++) {
-            float x = rows_src[i] * sc;
-            __half h = __float2half_rn(x);
-            dst_hi[i] = h; dst_lo[i] = __float2half_rn(x - __half2float(h));
-        }
-        (void)K;
-    }
     static float pow2_scale(const std::vector<float>& w, float& inv) {
         float mx = 0.f;
         for (float v : w) mx = std::max(mx, std::fabs(v));
@@ -583,53 +499,6 @@ public:
         e = std::max(-24, std::min(24, e));
         inv = std::ldexp(1.0f, -e);
         return std::ldexp(1.0f, e);
-    }
-
-    // Stacked recurrent weights for lstm_scan_tc_kernel: per gate CTA c, 128 rows = [hi of rows {g*H + 16c + u}; lo of the same],
-    // per projection slice r, 64 rows = [hi of W_hr rows 32r..32r+31 ; lo of the same].
-    void init_scan(const ModelWeights& w) {
-        const int D = d.D, H = d.H;
-        const int GC = H / scan::UNITS, RS = D / scan::PROWS;
-        scan_tc = (D % 64 == 0) && (H % 64 == 0) && (H % scan::UNITS == 0) && (D % scan::PROWS == 0) && (GC + RS * 4 <= num_sms) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
-        if (!scan_tc) return;
-        const size_t wbytes = std::max<size_t>((size_t)(D / 64) * 16384, (size_t)(H / 64) * 8192);
-        // shared-memory plan for the largest case (two groups of 32 sessions)
-        const int KBW = D / 64, KBH = H / 64;
-        const size_t smem_gate = 1024 + (size_t)KBW * 16384 + (size_t)scan::GSTAGES * 16384 + 128 * 33 * 4 + 128 + 2 * (size_t)32 * 256 + 2 * (size_t)32 * scan::UNITS * 4 + 512;
-        const size_t smem_proj = 1024 + (size_t)KBH * 8192 + (size_t)KBH * 4096 + 64 * 17 * 4 + 512;
-        scan_smem = std::max(smem_gate, smem_proj);
-        if (scan_smem > 227 * 1024 || KBH > 256) { scan_tc = false; return; }
-        CK(cudaFuncSetAttribute(scan::lstm_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-        for (auto& lw : w.layers) {
-            ScanLayer sl;
-            float sc_hh = pow2_scale(lw.w_hh, sl.inv_hh), sc_hr = pow2_scale(lw.w_hr, sl.inv_hr);
-            std::vector<__half> wg((size_t)GC * 128 * D), wp((size_t)RS * 64 * H);
-            for (int c = 0; c < GC; c++)
-                for (int g4 = 0; g4 < 4; g4++)
-                    for (int u = 0; u < scan::UNITS; u++) {
-                        const float* src = lw.w_hh.data() + ((size_t)g4 * H + (size_t)c * scan::UNITS + u) * D;
-                        __half* hi = wg.data() + ((size_t)c * 128 + g4 * 16 + u) * D;
-                        __half* lo = wg.data() + ((size_t)c * 128 + 64 + g4 * 16 + u) * D;
-                        for (int k = 0; k < D; k++) { float x = src[k] * sc_hh; __half hh = __float2half_rn(x); hi[k] = hh; lo[k] = __float2half_rn(x - __half2float(hh)); }
-                    }
-            for (int r = 0; r < RS; r++)
-                for (int i = 0; i < scan::PROWS; i++) {
-                    const float* src = lw.w_hr.data() + ((size_t)r * scan::PROWS + i) * H;
-                    __half* hi = wp.data() + ((size_t)r * 64 + i) * H;
-                    __half* lo = wp.data() + ((size_t)r * 64 + 32 + i) * H;
-                    for (int k = 0; k < H; k++) { float x = src[k] * sc_hr; __half hh = __float2half_rn(x); hi[k] = hh; lo[k] = __float2half_rn(x - __half2float(hh)); }
-                }
-            sl.wg = upload(wg); sl.wp = upload(wp);
-            sl.mapWg = make_map_2d(sl.wg, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 128, (uint64_t)D, 64, 128, true);
-            sl.mapWp = make_map_2d(sl.wp, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)RS * 64, (uint64_t)H, 64, 64, true);
-            slayers.push_back(sl);
-        }
-        // per group: h exchange [2][32][D], m exchange [2][32][H]
-        CK(cudaMalloc(&sx_h_hi, sizeof(__half) * 2 * 2 * 32 * (size_t)D)); sx_h_lo = nullptr;
-        CK(cudaMalloc(&sx_m_hi, sizeof(__half) * 2 * 2 * 32 * (size_t)H)); sx_m_lo = nullptr;
-        CK(cudaMemset(sx_m_hi, 0, sizeof(__half) * 2 * 2 * 32 * (size_t)H));
-        CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned)));
-        owned.push_back(sx_h_hi); owned.push_back(sx_m_hi); owned.push_back(scan_counters);
     }
 
     void dump_trace(int grid, int T, int GC) {
@@ -653,88 +522,6 @@ public:
         double mn = 1e30, mx = 0; for (int c = 0; c < GC; c++) { double v = at(c, T / 2, 7) - at(0, T / 2, 0); mn = std::min(mn, v); mx = std::max(mx, v); }
         double mn2 = 1e30, mx2 = 0; for (int c = GC; c < grid; c++) { double v = at(c, T / 2, 7) - at(0, T / 2, 0); mn2 = std::min(mn2, v); mx2 = std::max(mx2, v); }
         fprintf(stderr, "\n  gate release spread [%.0f, %.0f]  proj release spread [%.0f, %.0f]\n", mn, mx, mn2, mx2);
-    }
-
-    void init_scan2(const ModelWeights& w) {
-        const int D = d.D, H = d.H;
-        const char* sel = getenv("APRIL_B200_SCAN");
-        scan2 = (H % 64 == 0) && (H % scan2::UNITS == 0) && (H / scan2::UNITS <= num_sms) && (D % 8 == 0) && !(sel && !strcmp(sel, "v1")) && getenv("APRIL_B200_SIMT_SCAN") == nullptr;
-        if (!scan2) return;
-        const int KBH = H / 64, GC = H / scan2::UNITS;
-        scan2_smem = 1024 + (size_t)KBH * 8192 + (size_t)scan2::RSTAGES * 16384 + 64 * 65 * 4 + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + scan2::MAXG * 64 * 4 + 2 * scan2::EPI_WARPS * 32 * 2 + 512;
-        if (scan2_smem > 227 * 1024) { scan2 = false; return; }
-        CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan2_smem));
-        scan3_smem = 1024 + (size_t)(H / 128) * 16384 + (size_t)scan2::RSTAGES * 16384 + scan3::TEAMS * (64 * 33 * 4 + 64 * 36 * 4) + 256 + (size_t)64 * scan2::UNITS * 16 + (size_t)64 * scan2::UNITS * 4 + scan2::MAXG * 64 * 4 + scan3::TEAMS * 2 * scan2::EPI_WARPS * 32 * 2 + 512;   // groups of <= 32 sessions
-        scan3 = (H % 128 == 0) && scan3_smem <= 227 * 1024 && !(sel && !strcmp(sel, "v2"));
-        if (scan3) {
-            CK(cudaFuncSetAttribute(scan3::lstm_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan3_smem));
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan3::THREADS3); cfg.dynamicSmemBytes = scan3_smem; cfg.stream = st;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, scan3::lstm_scan3_kernel, &cfg) != cudaSuccess || ncl * 2 < GC) { cudaGetLastError(); scan3 = false; }   // all pairs must be co-resident
-        }
-        float *dA = nullptr, *dB = nullptr, *dC = nullptr;
-        CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
-        std::vector<float> weff((size_t)4 * H * H);
-        for (auto& lw : w.layers) {
-            Scan2Layer sl;
-            CK(cudaMemcpy(dA, lw.w_hh.data(), sizeof(float) * (size_t)4 * H * D, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(dB, lw.w_hr.data(), sizeof(float) * (size_t)D * H, cudaMemcpyHostToDevice));
-            scan2::weff_kernel<<<dim3((unsigned)((H + 15) / 16), (unsigned)((4 * H + 15) / 16)), 256, 0, st>>>(dA, dB, dC, 4 * H, H, D);
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(weff.data(), dC, sizeof(float) * weff.size(), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const float sc = pow2_scale(weff, sl.inv);
-            std::vector<__half> wg((size_t)GC * 64 * H);
-            if (scan3) {
-                // CTA c = pair * 2 + r: 128 stacked rows rho = hl * 64 + half * 32 + gate * 8 + u of units pair * 16 + half * 8 + u, K half r
-                const int KH = H / 2;
-                for (int c = 0; c < GC; c++)
-                    for (int rho = 0; rho < 128; rho++) {
-                        const int hl = rho >> 6, half = (rho >> 5) & 1, g4 = (rho >> 3) & 3, u = rho & 7, r = c & 1, pair = c >> 1;
-                        const float* src = weff.data() + ((size_t)g4 * H + (size_t)pair * 16 + half * 8 + u) * H + (size_t)r * KH;
-                        __half* dst = wg.data() + ((size_t)c * 128 + rho) * KH;
-                        for (int k = 0; k < KH; k++) {
-                            const float x = src[k] * sc; const __half hh = __float2half_rn(x);
-                            dst[k] = hl ? __float2half_rn(x - __half2float(hh)) : hh;
-                        }
-                    }
-                sl.w = upload(wg);
-                sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 128, (uint64_t)KH, 64, 128, true);
-            } else {
-            for (int c = 0; c < GC; c++)
-                for (int g4 = 0; g4 < 4; g4++)
-                    for (int u = 0; u < scan2::UNITS; u++) {
-                        const float* src = weff.data() + ((size_t)g4 * H + (size_t)c * scan2::UNITS + u) * H;
-                        __half* hi = wg.data() + ((size_t)c * 64 + g4 * 8 + u) * H;
-                        __half* lo = wg.data() + ((size_t)c * 64 + 32 + g4 * 8 + u) * H;
-                        for (int k = 0; k < H; k++) { float x = src[k] * sc; __half hh = __float2half_rn(x); hi[k] = hh; lo[k] = __float2half_rn(x - __half2float(hh)); }
-                    }
-            sl.w = upload(wg);
-            sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 64, (uint64_t)H, 64, 64, true);
-            }
-            sl.w_hr = make_tc_weight(lw.w_hr, D, H);
-            s2layers.push_back(sl);
-        }
-        CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
-        // largest cluster size whose clusters can all be co-resident (the kernel spin-waits across the grid)
-        scan2_cs = 1;
-        const char* cs_env = getenv("APRIL_B200_SCAN_CLUSTER");        // multicast is opt-in: it measured slower than plain loads
-        for (int cs : { 8, 4, 2 }) {
-            if (!cs_env || atoi(cs_env) != cs) continue;
-            if (GC % cs) continue;
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan2::THREADS); cfg.dynamicSmemBytes = scan2_smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int ncl = 0;
-            if (cs > 8) CK(cudaFuncSetAttribute(scan2::lstm_scan2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            if (cudaOccupancyMaxActiveClusters(&ncl, scan2::lstm_scan2_kernel, &cfg) == cudaSuccess && ncl * cs >= GC) { scan2_cs = cs; break; }
-            cudaGetLastError();
-        }
-        if (cs_env && atoi(cs_env) == 1) scan2_cs = 1;
-        if (!scan_counters) { CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned))); owned.push_back(scan_counters); }
     }
 
     // ---- wide-batch scan -------------------------------------------------------------------------------------
@@ -764,8 +551,6 @@ public:
 
     void init_scan4(const ModelWeights& w) {
         const int D = d.D, H = d.H;
-        const char* sel = getenv("APRIL_B200_SCAN");
-        if (sel && strcmp(sel, "v4")) return;                              // an older kernel was asked for
         if (H % 128 || H / scan4::UNITS > num_sms || D % 8) return;     // K slices are whole 64-wide k-blocks
         const int GC = H / scan4::UNITS;
         scan4_cs = 2; scan4_mmaw = 2;
@@ -831,94 +616,6 @@ public:
         }
     }
 
-    // one layer, steps [t0, t0+tc): single-exchange scan; writes m rows (Mall) for the layer-output GEMM
-    void scan2_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
-        const int H = d.H;
-        Scan2Layer& sl = s2layers[(size_t)l];
-        __half* Mx = b_mx.as<__half>();
-        scan2::scan2_prepare_kernel<<<64, 256, 0, st>>>(mw, Mx, B, H); launch_check();
-        for (int g0 = 0; g0 < B; g0 += 64) {
-            const int Bc = std::min(64, B - g0);
-            scan2::Scan2Args a{};
-            static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 2;   // measured: every tcgen05.mma costs >= ~84 clk to issue whatever its N, so more (smaller) groups cost more issue time
-            a.T = tc; a.t0 = t0;
-            a.NG = std::max(1, std::min({ groups_env, (int)scan2::MAXG, (Bc + 15) / 16 }));       // interleaved groups of >= 16 sessions
-            if (scan3) a.NG = std::max(a.NG, (Bc + 31) / 32);                                      // its exchange blocks hold <= 32 sessions per group
-            if (!scan3 && a.NG == 3) a.NG = Bc > 48 ? 4 : 2;                                                 // NG * Bp must stay <= 64
-            const int per = (Bc + a.NG - 1) / a.NG;
-            for (int g = 0, o = 0; g < scan2::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::min(per, Bc - o) : 0; o += a.Bg[g]; }
-            a.Bp = (per + 15) & ~15;
-            a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan2::UNITS;
-            const int KBH = H / 64;
-            const int KBW = scan3 ? KBH / 2 : KBH;                                                 // k-blocks a CTA walks per step
-            a.KBG = 1; for (int kk = 1; kk <= KBW; kk++) if (KBW % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
-            static const bool m64_env = !(getenv("APRIL_B200_SCAN_M128"));
-            static const bool norelay_env = getenv("APRIL_B200_SCAN_NORELAY") != nullptr;
-            a.dbg = norelay_env ? 0 : 4;     // bit 2: one handover poller per CTA, relayed to the other producer warps (-2.3 % measured)
-            a.m64 = m64_env ? 1 : 0;
-            a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.c_state = cw; a.m_state = mw;
-            a.Mx = Mx; a.Mall_hi = b_mall_h.as<__half>(); a.Mall_lo = b_mall_l.as<__half>(); a.counter = scan_counters;
-            static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
-            const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
-            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
-            CK(cudaMemsetAsync(scan_counters, 0, 256 * sizeof(unsigned), st));
-            CUtensorMap mMx = make_map_mx(Mx, (uint64_t)B, (uint64_t)H, (uint64_t)tc + 1, (uint32_t)a.Bp, (uint32_t)a.KBG);
-            CUtensorMap mG = make_map_g3(G, (uint64_t)tc * B, (uint64_t)H, scan2::UNITS, (uint32_t)a.Bp);
-            {
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan2::THREADS); cfg.dynamicSmemBytes = scan2_smem; cfg.stream = st;
-                cudaLaunchAttribute at[2];
-                at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-                at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = (unsigned)scan2_cs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-                cfg.attrs = at; cfg.numAttrs = 2;
-                if (scan3) { cfg.blockDim = dim3(scan3::THREADS3); cfg.dynamicSmemBytes = scan3_smem; cfg.numAttrs = 1; CK(cudaLaunchKernelEx(&cfg, scan3::lstm_scan3_kernel, sl.mapW, mMx, mG, a)); }   // cluster dims are compiled in
-                else CK(cudaLaunchKernelEx(&cfg, scan2::lstm_scan2_kernel, sl.mapW, mMx, mG, a));
-            }
-            launch_check();
-            if (do_trace) dump_trace(a.GC, tc, a.GC / 2);
-        }
-    }
-
-    // one layer, steps [t0, t0+tc) of this pass: the recurrent scan on tensor cores, 64 sessions (two interleaved groups of 32) per launch
-    void scan_layer_tc(int l, const float* G, float* Hout, float* hw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
-        const int D = d.D, H = d.H;
-        ScanLayer& sl = slayers[(size_t)l];
-        for (int g0 = 0; g0 < B; g0 += 64) {
-            const int Bc = std::min(64, B - g0);
-            scan::ScanArgs a{};
-            a.T = tc; a.t0 = t0; a.NG = Bc > 16 ? 2 : 1;
-            a.Bg[0] = a.NG == 2 ? (Bc + 1) / 2 : Bc; a.Bg[1] = Bc - a.Bg[0];
-            a.goff[0] = 0; a.goff[1] = a.Bg[0];
-            a.Bp = (a.Bg[0] + 15) & ~15;
-            a.Bs = B; a.g0 = g0; a.D = D; a.H = H;
-            a.GC = H / scan::UNITS; a.RS = D / scan::PROWS; a.BSP = a.Bp / 16;
-            const int KBW = D / 64, KBH = H / 64;
-            a.KBG = 1; for (int kk = 1; kk <= KBW; kk++) if (KBW % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
-            a.PC = KBH % 4 == 0 ? 4 : (KBH % 2 == 0 ? 2 : 1);
-            a.inv_scale_hh = sl.inv_hh; a.inv_scale_hr = sl.inv_hr;
-            a.nsteps = d_nsteps + g0; a.c_state = cw + (size_t)g0 * H; a.h_state = hw + (size_t)g0 * D;
-            for (int g = 0; g < scan::MAXG; g++) { a.h_x[g] = sx_h_hi + (size_t)g * 2 * 32 * D; a.m_x[g] = sx_m_hi + (size_t)g * 2 * 32 * H; }
-            a.Hout = Hout + (size_t)g0 * D; a.counters = scan_counters;
-            static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
-            const unsigned grid = (unsigned)(a.GC + a.NG * a.RS * a.BSP);
-            const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
-            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)grid * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)grid * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
-            for (int g = 0; g < a.NG; g++) { scan::scan_prepare_kernel<<<32, 256, 0, st>>>(a.h_state + (size_t)a.goff[g] * D, a.h_x[g], a.Bg[g], a.Bp, D); launch_check(); }
-            CK(cudaMemsetAsync(sx_m_hi, 0, sizeof(__half) * 2 * 2 * 32 * (size_t)H, st));
-            CK(cudaMemsetAsync(scan_counters, 0, 256 * sizeof(unsigned), st));
-            CUtensorMap mHx[2], mMx[2];
-            for (int g = 0; g < 2; g++) {
-                mHx[g] = make_map_kblocks_hl(a.h_x[g], (uint64_t)a.Bp, (uint64_t)D, (uint32_t)a.Bp, (uint32_t)a.KBG);
-                mMx[g] = make_map_kblocks_hl(a.m_x[g], (uint64_t)a.Bp, (uint64_t)H, 16, (uint32_t)(KBH / a.PC));
-            }
-            CUtensorMap mG = make_map_2d(G, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)tc * B, (uint64_t)4 * H, 16, (uint32_t)a.Bp, false);
-            void* args[] = { &sl.mapWg, &sl.mapWp, &mHx[0], &mHx[1], &mMx[0], &mMx[1], &mG, &a };
-            CK(cudaLaunchCooperativeKernel((const void*)scan::lstm_scan_tc_kernel, dim3(grid), dim3(scan::THREADS), args, scan_smem, st));
-            launch_check();
-            if (do_trace) dump_trace((int)grid, tc, a.GC);
-        }
-    }
-
     // the radix-8 front-end serves the 512-sample window (every model of the reference: 25 ms at 16 kHz); other windows take the generic kernel
     bool fbank512() const { static const bool generic = getenv("APRIL_B200_FBANK") && !strcmp(getenv("APRIL_B200_FBANK"), "generic"); return frame_N == k::FB3_N && !generic; }
     static constexpr size_t kFbank512Smem = 4 * 2 * k::FB3_PITCH * sizeof(double);
@@ -939,16 +636,14 @@ public:
         else if (epi == tc::GE_F32_RESIDUAL_SPLIT) gemm_tc_launch<NP, tc::GE_F32_RESIDUAL_SPLIT, CL>(grid, mAh, mAl, mBh, mBl, g);
         else gemm_tc_launch<NP, tc::GE_DSWISH_SPLIT, CL>(grid, mAh, mAl, mBh, mBl, g);
     }
-    void set_gemm_attrs() {}
 
     // C = A * W^T (+bias, epilogue) on the tensor cores. A given as fp16 (hi, lo) [M, K].
     void gemm_tc(int epi, const __half* a_hi, const __half* a_lo, const TcWeight& w, const float* bias, const float* residual,
                  float* out_f32, __half* out_hi, __half* out_lo, int M, int cls = 0) {
         span_begin(cls);
         if (profile) { stat.gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; stat.gemm_launches++; if (cls == 3) stat.lstm_gemm_flops += 2.0 * (double)M * (double)w.N * (double)w.K; }
-        static const bool pair_env = getenv("APRIL_B200_GEMM_CLUSTER") == nullptr || atoi(getenv("APRIL_B200_GEMM_CLUSTER")) != 1;
         const int tiles_m = (M + tc::GEMM_BM - 1) / tc::GEMM_BM, tiles_n = (w.N + tc::GEMM_BN - 1) / tc::GEMM_BN;
-        const bool pair = pair_env && tiles_m >= 2;          // CTA pairs (cta_group::2): each CTA ingests its A rows and half of the B rows
+        const bool pair = tiles_m >= 2;          // CTA pairs (cta_group::2): each CTA ingests its A rows and half of the B rows
         CUtensorMap mAh = make_map_f16(a_hi, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM), mAl = make_map_f16(a_lo, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM);
         const uint32_t bbox = pair ? tc::GEMM_BN / 2 : tc::GEMM_BN;
         CUtensorMap mBh = make_map_f16(w.hi, (uint64_t)w.N, (uint64_t)w.K, bbox), mBl = make_map_f16(w.lo, (uint64_t)w.N, (uint64_t)w.K, bbox);
@@ -978,7 +673,7 @@ public:
         else {
             if (K % 8 || N % 8) return -1;
             const int saved = npass;
-            npass = tier; set_gemm_attrs();
+            npass = tier;
             std::vector<float> wv(W, W + (size_t)N * K);
             TcWeight tw = make_tc_weight(wv, N, K);
             dAh.ensure(sizeof(__half) * (size_t)M * K); dAl.ensure(sizeof(__half) * (size_t)M * K);
@@ -1189,11 +884,7 @@ public:
             b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
             b_eo.ensure(sizeof(float) * Mc * J);
             const bool use_s4 = npass && scan4;
-            const bool use_s2 = npass && (scan2 || scan4);
             if (use_s4) { b_mall_h.ensure(sizeof(__half) * (Mc + (size_t)B) * H); b_mall_l.ensure(sizeof(__half) * (Mc + (size_t)B) * H); }
-            else if (use_s2) {
-                b_mx.ensure(sizeof(__half) * ((size_t)Tc + 1) * 2 * B * H); b_mall_h.ensure(sizeof(__half) * Mc * H); b_mall_l.ensure(sizeof(__half) * Mc * H);
-            }
             b_mw.ensure(sizeof(float) * (size_t)L * B * H);
             if (npass) {
                 b_xe_h.ensure(sizeof(__half) * Mc * KE); b_xe_l.ensure(sizeof(__half) * Mc * KE);
@@ -1212,7 +903,7 @@ public:
             k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
             k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
             float* Mw = b_mw.as<float>();
-            if (use_s2) { k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
+            if (use_s4) { k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
             const size_t greedy_smem = sizeof(float) * (size_t)(3 * J + d.E);
             for (int t0 = 0; t0 < Tmax; t0 += Tc) {
                 const int tc = std::min(Tc, Tmax - t0);
@@ -1242,8 +933,6 @@ public:
                     float* cw = Cw + (size_t)l * B * H;
                     span_begin(1);
                     if (use_s4) scan4_layer(l, G, Mw + (size_t)l * B * H, cw, d_nsteps, t0, tc, B);
-                    else if (use_s2) scan2_layer(l, G, Mw + (size_t)l * B * H, cw, d_nsteps, t0, tc, B);
-                    else if (npass && scan_tc) scan_layer_tc(l, G, Hout, hw, cw, d_nsteps, t0, tc, B);
                     else for (int t = 0; t < tc; t++) {
                         k::lstm_gates_kernel<<<dim3((unsigned)(H / 16), (unsigned)((B + 63) / 64)), 256, 0, st>>>(
                             G + (size_t)t * B * 4 * H, hw, w.w_hh, cw, Ms, d_nsteps, t0 + t, B, D, H);
@@ -1261,8 +950,8 @@ public:
                         k::basic_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, M, D, w.norm_eps); launch_check();
                     } else {
                         const TcLayer& tl = tlayers[(size_t)l];
-                        const size_t moff = use_s4 ? (size_t)B * H : 0;   // scan4: row block 0 of the m planes is the initial state
-                        if (use_s2) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>() + moff, b_mall_l.as<__half>() + moff, (use_s4 ? s4layers[(size_t)l].w_hr : s2layers[(size_t)l].w_hr), nullptr, X, X1, X1_h, X1_l, M, 3);   // x + W_hr m
+                        const size_t moff = (size_t)B * H;                // row block 0 of the m planes is the initial state
+                        if (use_s4) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>() + moff, b_mall_l.as<__half>() + moff, s4layers[(size_t)l].w_hr, nullptr, X, X1, X1_h, X1_l, M, 3);   // x + W_hr m
                         else { tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check(); }
                         gemm_tc(tc::GE_DSWISH_SPLIT, X1_h, X1_l, tl.ff1, w.ff1_b, nullptr, nullptr, F1_h, F1_l, M);
                         gemm_tc(tc::GE_F32_RESIDUAL, F1_h, F1_l, tl.ff2, w.ff2_b, X1, X2, nullptr, nullptr, M);
@@ -1298,7 +987,7 @@ public:
             }
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
-            if (use_s2) { k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
+            if (use_s4) { k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
             p_rec.ensure(rec_bytes); p_np.ensure(np_bytes);
             CK(cudaMemcpyAsync(p_rec.p, b_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(p_np.p, b_np.p, np_bytes, cudaMemcpyDeviceToHost, st));

@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--ragged", type=int, default=1)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--a", default="APRIL_B200_SCAN=v3", help="space-separated VAR=VALUE list of arm A")
+    ap.add_argument("--a", default="APRIL_B200_SCAN=simt", help="space-separated VAR=VALUE list of arm A")
     ap.add_argument("--b", default="", help="arm B")
     ap.add_argument("--oracle", type=int, default=0, help="also run the first N sessions through the oracle")
     ap.add_argument("--child", default=None)
