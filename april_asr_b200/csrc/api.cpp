@@ -64,6 +64,7 @@ struct Lane {
     bool leader_active = false;
     int live_sync = 0;                           // synchronous sessions placed on this lane
     int miss_streak = 0;                         // consecutive windows that caught nobody
+    long last_pass_us = 0;                       // smoothed duration of this lane's coalesced passes
     // asynchronous sessions: one batcher thread per GPU (replaces one ProcThread per session, src/proc_thread.c:138-172)
     std::mutex amu;
     std::condition_variable acv;
@@ -154,18 +155,21 @@ static void sync_submit(AprilASRSession_i* s, const int16_t* pcm, size_t count, 
         if (L.leader_active) { L.qcv.wait(lk); continue; }
         L.leader_active = true;                              // I lead: my request is in the queue, so it is part of my batch
         // Coalescing window: wait while callers keep arriving — until every live synchronous session of this GPU has a call queued,
-        // or nobody new came for `win` microseconds, or 20 windows have passed. 256 threads released by the same 40 ms audio tick
-        // arrive over a few hundred microseconds; a lone caller among many idle sessions pays one window.
+        // or nobody new came for a quiet interval, or the cap is reached. The interval scales with what a pass costs (an eighth of
+        // the last pass, at least `coalesce_us`): 256 threads released by the same 40 ms audio tick arrive over a few hundred
+        // microseconds in bursts, and one more pass for the stragglers costs far more than waiting for them; a lone caller among
+        // many idle sessions pays one interval.
         const long win = L.model->coalesce_us;
         if (win > 0 && (int)L.queue.size() < L.live_sync && L.miss_streak < 4) {
-            const auto cap = std::chrono::steady_clock::now() + std::chrono::microseconds(20 * win);
+            const long quiet = std::max(win, L.last_pass_us / 8), cap_us = std::max(10 * win, L.last_pass_us / 2);
+            const auto cap = std::chrono::steady_clock::now() + std::chrono::microseconds(cap_us);
             for (;;) {
                 const size_t seen = L.queue.size();
                 if ((int)seen >= L.live_sync) break;
                 const auto now = std::chrono::steady_clock::now();
                 if (now >= cap) break;
-                L.qcv.wait_until(lk, std::min(cap, now + std::chrono::microseconds(win)));
-                if (L.queue.size() == seen && std::chrono::steady_clock::now() >= now + std::chrono::microseconds(win)) break;   // a quiet window
+                L.qcv.wait_until(lk, std::min(cap, now + std::chrono::microseconds(quiet)));
+                if (L.queue.size() == seen && std::chrono::steady_clock::now() >= now + std::chrono::microseconds(quiet)) break;   // a quiet interval
             }
         }
         std::vector<SyncReq*> batch;
@@ -175,9 +179,12 @@ static void sync_submit(AprilASRSession_i* s, const int16_t* pcm, size_t count, 
         lk.unlock();
         std::vector<PassItem> items(batch.size());
         for (size_t i = 0; i < batch.size(); i++) items[i] = std::move(batch[i]->item);
+        const auto p0 = std::chrono::steady_clock::now();
         L.engine->run_pass(items);
+        const long pass_us = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - p0).count();
         for (size_t i = 0; i < batch.size(); i++) batch[i]->item = std::move(items[i]);
         lk.lock();
+        L.last_pass_us = (3 * L.last_pass_us + pass_us) / 4;
         for (auto* b : batch) b->done = true;
         L.leader_active = false;
         L.qcv.notify_all();                                  // wakes my batch (done) and, if calls queued up meanwhile, the next leader

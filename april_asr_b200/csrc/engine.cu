@@ -15,6 +15,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_scan4.cuh"
+#include "kernels_scan3.cuh"
 #include "kernels_greedy_tc.cuh"
 
 namespace april {
@@ -73,6 +74,32 @@ static CUtensorMap make_map_2d(const void* ptr, CUtensorMapDataType dt, size_t e
     CUresult r = get_encode_tiled()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled failed: %d\n", (int)r); abort(); }
+    return m;
+}
+
+// 3-D view of the gate pre-activations G [rows, 4H] fp32: {unit, gate, row}; one box = 8 units x 4 gates x box_rows rows
+static CUtensorMap make_map_g3(const void* ptr, uint64_t rows, uint64_t H, uint32_t box_units, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = { H, 4, rows };
+    cuuint64_t strides[2] = { H * sizeof(float), 4 * H * sizeof(float) };
+    cuuint32_t box[3] = { box_units, 4, box_rows };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (G 3-D) failed: %d\n", (int)r); abort(); }
+    return m;
+}
+
+// 5-D view of the two m planes [2][(T + 1) * Bs][H] fp16: {64-wide k-block element, session, hi | lo plane, k-block, time}
+static CUtensorMap make_map_mx(const void* ptr, uint64_t Bs, uint64_t H, uint64_t Trows, uint64_t plane_elems, uint32_t box_sessions, uint32_t box_kb) {
+    CUtensorMap m;
+    cuuint64_t dims[5] = { 64, Bs, 2, H / 64, Trows };
+    cuuint64_t strides[4] = { H * sizeof(__half), plane_elems * sizeof(__half), 64 * sizeof(__half), Bs * H * sizeof(__half) };
+    cuuint32_t box[5] = { 64, box_sessions, 2, box_kb, 1 };
+    cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "libapril: (engine) [ERROR] cuTensorMapEncodeTiled (5-D) failed: %d\n", (int)r); abort(); }
     return m;
 }
 
@@ -163,13 +190,16 @@ public:
     std::vector<TcLayer> tlayers;
     bool gemm_attr[16] = {};
     // wide-batch scan (kernels_scan4.cuh): sessions on the UMMA M dimension, K split over clusters of scan4_cs CTAs
-    struct Scan4Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; };
+    struct Scan4Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; __half* w3 = nullptr; CUtensorMap mapW3; };   // w3: the same W_eff in the small-batch kernel's layout
     std::vector<Scan4Layer> s4layers;
     bool scan4 = false;
     int scan4_cs = 2, scan4_mmaw = 2;
     size_t scan4_smem = 0;
+    bool scan3 = false;             // small-batch kernel (kernels_scan3.cuh) available: used for passes of <= 64 sessions
+    size_t scan3_smem = 0;
+    size_t mall_rows = 0;           // rows per m plane of the current pass chunking: (Tc + 1) * B
     float* m_store = nullptr;       // [slot][L][H]
-    DevBuf b_mall_h, b_mall_l, b_mw;
+    DevBuf b_mall, b_mw;            // b_mall: the two m planes [2][(Tc + 1) * B][H] fp16
     unsigned* scan_counters = nullptr;
     DevBuf b_trace;
     DevBuf b_xe_h, b_xe_l, b_x_h, b_x_l, b_x1_h, b_x1_l, b_f1_h, b_f1_l;
@@ -556,6 +586,17 @@ public:
         scan4_cs = 2; scan4_mmaw = 2;
         const bool ok = scan4_prepare_variant<2, 2>(GC);
         if (!ok) return;
+        {   // the small-batch kernel: all pairs co-resident, groups of <= 32 sessions
+            scan3_smem = 1024 + (size_t)(H / 128) * 16384 + (size_t)scan3::RSTAGES * 16384 + scan3::TEAMS * (64 * 33 * 4 + 64 * 36 * 4) + 256 + (size_t)64 * scan3::UNITS * 16 + (size_t)64 * scan3::UNITS * 4 + scan3::MAXG * 64 * 4 + scan3::TEAMS * 2 * scan3::EPI_WARPS * 32 * 2 + 512;
+            scan3 = scan3_smem <= 227 * 1024 && cudaFuncSetAttribute(scan3::lstm_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan3_smem) == cudaSuccess;
+            if (scan3) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan3::THREADS3); cfg.dynamicSmemBytes = scan3_smem; cfg.stream = st;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, scan3::lstm_scan3_kernel, &cfg) != cudaSuccess || ncl * 2 < GC) scan3 = false;
+            }
+            cudaGetLastError();
+        }
         const int CS = scan4_cs, NC = 32 * CS, Kc = H / CS;
         float *dA = nullptr, *dB = nullptr, *dC = nullptr;
         CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
@@ -575,6 +616,13 @@ public:
             CK(cudaStreamSynchronize(st));
             sl.mapW = make_map_2d(sl.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 2 * NC, (uint64_t)Kc, 64, (uint32_t)NC, true);
             sl.w_hr = make_tc_weight(lw.w_hr, D, H);
+            if (scan3) {
+                CK(cudaMalloc(&sl.w3, sizeof(__half) * (size_t)GC * 128 * (H / 2))); owned.push_back(sl.w3);
+                scan3::pack_weff3_kernel<<<dim3((unsigned)GC, 128), 128, 0, st>>>(dC, sl.w3, H, sc);
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(st));
+                sl.mapW3 = make_map_2d(sl.w3, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 128, (uint64_t)(H / 2), 64, 128, true);
+            }
             s4layers.push_back(sl);
         }
         CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
@@ -582,22 +630,55 @@ public:
         scan4 = true;
     }
 
+    // small batches (<= 64 sessions): two interleaved groups of <= 32 sessions through the latency-optimised pair kernel
+    void scan3_layer(const Scan4Layer& sl, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B, __half* Mx, size_t plane, int l) {
+        const int H = d.H;
+        scan3::Scan2Args a{};
+        a.T = tc; a.t0 = t0;
+        a.NG = std::max((B + 31) / 32, std::min(2, (B + 15) / 16));        // groups of <= 32 sessions; two groups from 17 sessions on
+        const int per = (B + a.NG - 1) / a.NG;
+        for (int g = 0, o = 0; g < scan3::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::min(per, B - o) : 0; o += a.Bg[g]; }
+        a.Bp = (per + 15) & ~15;
+        a.Bs = B; a.g0 = 0; a.H = H; a.GC = H / scan3::UNITS;
+        const int KBW = H / 128;                                            // k-blocks a CTA walks per step (its K half)
+        a.KBG = 1; for (int kk = 1; kk <= KBW; kk++) if (KBW % kk == 0 && (size_t)kk * 2 * a.Bp * 128 <= 16384) a.KBG = kk;
+        a.dbg = 4;
+        a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.c_state = cw; a.m_state = mw;
+        a.Mx = Mx; a.plane = plane; a.counter = scan_counters;
+        static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
+        const bool do_trace = want_trace && l == 0 && tc >= 64;
+        if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
+        CK(cudaMemsetAsync(scan_counters, 0, 256 * sizeof(unsigned), st));
+        const CUtensorMap mMx = make_map_mx(Mx, (uint64_t)B, (uint64_t)H, (uint64_t)tc + 1, (uint64_t)plane, (uint32_t)a.Bp, (uint32_t)a.KBG);
+        const CUtensorMap mG = make_map_g3(G, (uint64_t)tc * B, (uint64_t)H, scan3::UNITS, (uint32_t)a.Bp);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan3::THREADS3); cfg.dynamicSmemBytes = scan3_smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = capturing ? 0 : 1;                   // cluster dims are compiled in
+        CK(cudaLaunchKernelEx(&cfg, scan3::lstm_scan3_kernel, sl.mapW3, mMx, mG, a));
+        launch_check();
+        if (do_trace) dump_trace(a.GC, tc, a.GC / 2);
+    }
+
     // one layer, steps [t0, t0+tc) of all B sessions of the pass: up to 512 sessions (4 groups of <= 128) per launch
     void scan4_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int H = d.H;
         const Scan4Layer& sl = s4layers[(size_t)l];
-        __half *Mh = b_mall_h.as<__half>(), *Ml = b_mall_l.as<__half>();
+        const size_t plane = ((size_t)mall_rows) * H;                      // elements per m plane (sized by run_pass)
+        __half *Mh = b_mall.as<__half>(), *Ml = Mh + plane;
         const size_t n0 = (size_t)B * H;
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
+        if (scan3 && B <= 64) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
         const int per_launch = scan4::MAXG * scan4::GROUP;
         for (int g0 = 0; g0 < B; g0 += per_launch) {
             const int Bc = std::min(per_launch, B - g0);
             scan4::Args a{};
             a.T = tc; a.t0 = t0;
-            // a group costs a full M = 128 set of MMAs whatever its size and every group walks the same dependent chain, so a batch is
-            // split only when it does not fit one group
-            a.NG = (Bc + scan4::GROUP - 1) / scan4::GROUP;
+            // two epilogue teams (groups k, k + 2): an even number of groups keeps both busy (measured: 128 sessions as 2 x 64 take 10.8 us
+            // per layer-step, as 1 x 128 11.8 us)
+            a.NG = Bc > 2 * scan4::GROUP ? 4 : (Bc >= 16 ? 2 : 1);
             if (groups_env >= (Bc + scan4::GROUP - 1) / scan4::GROUP && groups_env <= scan4::MAXG && Bc >= 8 * groups_env) a.NG = groups_env;
             const int per = ((Bc + a.NG - 1) / a.NG + 7) & ~7;
             for (int g = 0, o = 0; g < scan4::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::max(0, std::min(per, Bc - o)) : 0; o += a.Bg[g]; }
@@ -884,7 +965,7 @@ public:
             b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
             b_eo.ensure(sizeof(float) * Mc * J);
             const bool use_s4 = npass && scan4;
-            if (use_s4) { b_mall_h.ensure(sizeof(__half) * (Mc + (size_t)B) * H); b_mall_l.ensure(sizeof(__half) * (Mc + (size_t)B) * H); }
+            if (use_s4) { mall_rows = Mc + (size_t)B; b_mall.ensure(sizeof(__half) * 2 * mall_rows * H); }
             b_mw.ensure(sizeof(float) * (size_t)L * B * H);
             if (npass) {
                 b_xe_h.ensure(sizeof(__half) * Mc * KE); b_xe_l.ensure(sizeof(__half) * Mc * KE);
@@ -951,7 +1032,7 @@ public:
                     } else {
                         const TcLayer& tl = tlayers[(size_t)l];
                         const size_t moff = (size_t)B * H;                // row block 0 of the m planes is the initial state
-                        if (use_s4) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall_h.as<__half>() + moff, b_mall_l.as<__half>() + moff, s4layers[(size_t)l].w_hr, nullptr, X, X1, X1_h, X1_l, M, 3);   // x + W_hr m
+                        if (use_s4) gemm_tc(tc::GE_F32_RESIDUAL_SPLIT, b_mall.as<__half>() + moff, b_mall.as<__half>() + mall_rows * H + moff, s4layers[(size_t)l].w_hr, nullptr, X, X1, X1_h, X1_l, M, 3);   // x + W_hr m
                         else { tc::add_rows_split_kernel<<<ew_grid, 256, 0, st>>>(X, Hout, X1, X1_h, X1_l, (size_t)M * D); launch_check(); }
                         gemm_tc(tc::GE_DSWISH_SPLIT, X1_h, X1_l, tl.ff1, w.ff1_b, nullptr, nullptr, F1_h, F1_l, M);
                         gemm_tc(tc::GE_F32_RESIDUAL, F1_h, F1_l, tl.ff2, w.ff2_b, X1, X2, nullptr, nullptr, M);
@@ -970,7 +1051,17 @@ public:
                     ga.inv_scale = gt_inv; ga.bias = jp.join_b; ga.vflags = jp.vflags; ga.dtab = dtab; ga.enc_out = EO; ga.nsteps = d_nsteps; ga.slot = d_slot; ga.flush_flag = d_flush;
                     ga.gstate = gstate; ga.rec = b_rec.as<k::DecisionRecord>(); ga.npass = b_np.as<int>(); ga.tap_logits = want_tap ? b_tap.as<float>() : nullptr;
                     const int ncl = (B + ga.S - 1) / ga.S;
+                    static const bool gt_trace = getenv("APRIL_B200_GREEDY_TRACE") != nullptr;
+                    if (gt_trace) { ga.trace_cap = 512; b_trace.ensure(8 * 8 * 512); CK(cudaMemsetAsync(b_trace.p, 0, 8 * 8 * 512, st)); ga.trace = b_trace.as<unsigned long long>(); }
                     gt::joiner_greedy_tc_kernel<<<ncl * gt::CLUSTER, gt::THREADS, gt_smem, st>>>(gt_mapW, ga);
+                    if (gt_trace) {
+                        std::vector<unsigned long long> h(8 * 512);
+                        CK(cudaStreamSynchronize(st));
+                        CK(cudaMemcpy(h.data(), b_trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+                        double acc[8] = { 0 }; int n = 0; double per = 0;
+                        for (int p = 50; p < 450; p++) { if (!h[(size_t)p * 8] || !h[(size_t)(p + 1) * 8]) continue; for (int k2 = 0; k2 < 8; k2++) acc[k2] += (double)h[(size_t)p * 8 + k2] - (double)h[(size_t)p * 8]; per += (double)h[(size_t)(p + 1) * 8] - (double)h[(size_t)p * 8]; n++; }
+                        if (n) { fprintf(stderr, "greedy trace (ns from pass start, avg of %d passes; pass = %.0f ns): ", n, per / n); for (int k2 = 0; k2 < 8; k2++) fprintf(stderr, "%d:%.0f ", k2, acc[k2] / n); fprintf(stderr, "\n"); }
+                    }
                 } else if (fast_greedy) {
                     const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
                     const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));

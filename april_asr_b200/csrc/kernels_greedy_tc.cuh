@@ -53,6 +53,8 @@ struct Args {
     DecisionRecord* rec;          // [B][Tcap][3]
     int* npass;                   // [B][Tcap]
     float* tap_logits;            // [B][Tcap][3][V] or null
+    unsigned long long* trace;    // dev: [passes][8] globaltimer stamps of cluster 0 / rank 0, or null
+    int trace_cap;
 };
 
 static inline size_t smem_bytes(int J, int V) {
@@ -75,6 +77,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtimer_() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GT_TRACE(slot_) do { if (a.trace && blockIdx.x == 0 && (int)pc < a.trace_cap) a.trace[(size_t)pc * 8 + (slot_)] = gtimer_(); } while (0)
 __device__ __forceinline__ void build_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BUILD_WARPS * 32) : "memory"); }
 
 // grid = clusters * 8 CTAs, cluster dims (8,1,1); mapW: 2-D [8 * 2 * 64, J] fp16 = per rank [hi rows ; lo rows], box {64, 64}
@@ -143,6 +147,7 @@ joiner_greedy_tc_kernel(const __grid_constant__ CUtensorMap mapW, Args a) {
         }
         __syncthreads();
         for (int pass = 0; pass < 3; pass++, pc++) {
+            if (threadIdx.x == 0) GT_TRACE(0);
             if (warp < BUILD_WARPS) {
                 // ---- A: z = tanh(e + d) for the sessions still in this step, as fp16 (hi, lo) 128B-swizzled K-major rows
                 const int cps = J / 8;                                    // 16-byte chunks per session row
@@ -165,8 +170,9 @@ joiner_greedy_tc_kernel(const __grid_constant__ CUtensorMap mapW, Args a) {
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy tile stores -> the tensor core's (async proxy) reads
                 tc_fence_before();                                        // and my tcgen05.ld of the previous pass precede the next MMAs
+                if (threadIdx.x == 0) GT_TRACE(1);
                 build_bar_sync();
-                if (threadIdx.x == 0) mbar_arrive(afull_bar);
+                if (threadIdx.x == 0) { mbar_arrive(afull_bar); GT_TRACE(2); }
             } else {
                 // ---- B: logits of my 64 rows for all 32 session lanes: warp mw issues K-slice mw of every k-block into its accumulator
                 const int mw = warp - BUILD_WARPS;
@@ -183,6 +189,7 @@ joiner_greedy_tc_kernel(const __grid_constant__ CUtensorMap mapW, Args a) {
                         umma_f16(d_tmem, al, bh, idesc, 1u);
                     }
                     umma_commit(tfull_bar);
+                    if (mw == 0) GT_TRACE(3);
                 }
                 __syncwarp();
             }
@@ -190,6 +197,7 @@ joiner_greedy_tc_kernel(const __grid_constant__ CUtensorMap mapW, Args a) {
             const int parity = (int)(pc & 1);
             if (warp == 0) {
                 mbar_wait(tfull_bar, pc & 1);
+                if (lane == 0) GT_TRACE(4);
                 tc_fence_after();
                 const int s = lane;
                 float bv = (float)(-9999999999.0); int bi = -1; float blank_v = 0.f; int has_blank = 0;     // april_session.c:311-312
@@ -221,7 +229,9 @@ joiner_greedy_tc_kernel(const __grid_constant__ CUtensorMap mapW, Args a) {
                     for (uint32_t r = 0; r < CLUSTER; r++) st_remote_v4(slot_addr, r, bv, (float)bi, blank_v, has_blank ? 1.f : 0.f);
                 }
             }
+            if (threadIdx.x == 0) GT_TRACE(5);
             cluster_sync_();                                              // every CTA's partials have landed everywhere
+            if (threadIdx.x == 0) GT_TRACE(6);
             // ---- D: every CTA evaluates the same rule on the same 8 partials (replicated state)
             if (threadIdx.x < ns && !s_done[threadIdx.x]) {
                 const int s = threadIdx.x;
@@ -243,6 +253,7 @@ joiner_greedy_tc_kernel(const __grid_constant__ CUtensorMap mapW, Args a) {
                 if (is_blank) s_done[s] = 1;
             }
             __syncthreads();
+            if (threadIdx.x == 0) GT_TRACE(7);
             bool all_done = true;
             for (int s = 0; s < ns; s++) all_done &= (s_done[s] != 0);
             if (all_done) { pc++; break; }

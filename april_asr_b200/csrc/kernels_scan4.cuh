@@ -31,8 +31,8 @@ constexpr int UNITS = 8;          // hidden units whose cell update a CTA owns
 constexpr int GROUP = 128;        // sessions per group = UMMA M
 constexpr int MAXG = 4;           // interleaved groups per launch (512 sessions)
 constexpr int EPI_WARPS = 8;      // warps per epilogue team: two per TMEM lane quarter, each takes 4 of the CTA's 8 units
-constexpr int TEAMS = 1;          // epilogue teams (team k serves groups k, k + TEAMS). Measured on B200: a second team changes nothing
-                                  // (22.3 vs 23.5 us per 512-session layer-step): the ring, not the epilogue, paces the kernel
+constexpr int TEAMS = 2;          // epilogue teams: team k serves groups k, k + 2 (measured on B200 with one team: the TMEM drain,
+                                  // pair exchange and cell update of an item keep a team busy ~5.5 us, longer than the item's MMAs)
 constexpr uint32_t TILE_BYTES = GROUP * 128u;   // [128 sessions x 64 k] fp16, 128B-swizzled
 
 struct Args {
@@ -98,19 +98,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 
 template <int CS, int MMAW> struct Cfg {
     static constexpr int NC = 32 * CS;                          // W rows of the cluster = UMMA N: [owner rank p][unit half hc][gate][4 units]
-    // Activation ring: measured on B200, a tile is back in service ~1 us after its TMA was issued (L2 landing 0.65 us + MMAs + commit +
-    // barrier hops) whatever its size, so what a CTA ingests is (bytes in flight) / 1 us: the ring is as deep as shared memory allows
-    // (80 KB) and its stages are exactly one tile of the launch's group size (Bp x 128 B): 5 stages for 128-session groups, 16 for <= 40.
-    static constexpr uint32_t RING_BYTES = 80u * 1024u;
-    static constexpr int MAXST = 16;
-    static constexpr int XBUF = 1;                              // exchange block buffers (16 KB per source rank)
+    static constexpr int RST = CS == 2 ? 4 : 3;                 // ring stages (16 KB tiles)
+    static constexpr int XBUF = CS == 2 ? 2 : 1;                // exchange block buffers
     static constexpr int NSLOT = (512 / (MMAW * NC)) > 4 ? 4 : (512 / (MMAW * NC));   // accumulator sets in TMEM
-    static constexpr int WARPS = 1 + MMAW + TEAMS * EPI_WARPS + 1;   // producer, MMA issuers, epilogue team(s), releaser
+    static constexpr int WARPS = 1 + MMAW + TEAMS * EPI_WARPS + 1;   // producer, MMA issuers, epilogue teams, releaser (20 warps with MMAW = 2: five per
+                                                                     // scheduler, i.e. 96 registers per thread)
     static constexpr int THREADS = WARPS * 32;
     static constexpr uint32_t XSRC_BYTES = 2u * 4u * GROUP * 16u;   // one source rank's block: [hc][16-byte chunk][session] = 16 KB
     static constexpr uint32_t XB_BYTES = (CS - 1) * XSRC_BYTES;
-    // the M = 128 MMA reads 16 KB from a stage's base whatever Bp: the last stage over-reads into the exchange block (>= 15 KB) behind the ring
-    static size_t smem_bytes(int H) { return 1024 + (size_t)H * 128 + (size_t)RING_BYTES + (size_t)XBUF * XB_BYTES + 512; }
+    static size_t smem_bytes(int H) { return 1024 + (size_t)H * 128 + (size_t)RST * TILE_BYTES + (size_t)XBUF * XB_BYTES + 512; }
 };
 
 #define TRACE4(slot_) do { if (a.trace && g == 0) a.trace[((size_t)blockIdx.x * a.T + t) * 8 + (slot_)] = gtimer(); } while (0)
@@ -123,7 +119,7 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                   const __grid_constant__ CUtensorMap mapMlo,
                   Args a) {
     using C = Cfg<CS, MMAW>;
-    constexpr int NC = C::NC, XBUF = C::XBUF, NSLOT = C::NSLOT, MAXST = C::MAXST;
+    constexpr int NC = C::NC, RST = C::RST, XBUF = C::XBUF, NSLOT = C::NSLOT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -136,13 +132,11 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
     const uint32_t WT = (uint32_t)NC * 128u;                              // one W k-block tile
     const uint32_t whi0 = base, wlo0 = base + (uint32_t)KB * WT, WBYTES = 2u * (uint32_t)KB * WT;
     const uint32_t ring0 = base + WBYTES;
-    const uint32_t stage_bytes = (uint32_t)a.Bp * 128u;                   // one tile: [Bp sessions x 64 k] fp16
-    const int RST = min(MAXST, (int)(C::RING_BYTES / stage_bytes));       // ring stages of this launch
-    const uint32_t exr0 = ring0 + C::RING_BYTES;
+    const uint32_t exr0 = ring0 + RST * TILE_BYTES;
     const uint32_t bar0 = exr0 + XBUF * C::XB_BYTES;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (MAXST + s); };
-    const uint32_t wfull_bar = bar0 + 8u * (2 * MAXST);
+    auto empty_bar = [&](int s) { return bar0 + 8u * (RST + s); };
+    const uint32_t wfull_bar = bar0 + 8u * (2 * RST);
     auto tfull_bar = [&](int s) { return wfull_bar + 8u + 8u * s; };
     auto tempty_bar = [&](int s) { return wfull_bar + 8u + 8u * (4 + s); };
     auto rel_bar = [&](int g) { return wfull_bar + 8u + 8u * (8 + g); };
@@ -151,7 +145,7 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
     const uint32_t tmem_slot = wfull_bar + 8u + 8u * 16;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MAXST; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MMAW); }
+        for (int s = 0; s < RST; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MMAW); }
         mbar_init(wfull_bar, 1);
         for (int s = 0; s < 4; s++) { mbar_init(tfull_bar(s), MMAW); mbar_init(tempty_bar(s), EPI_WARPS); }
         for (int g = 0; g < MAXG; g++) mbar_init(rel_bar(g), EPI_WARPS);
@@ -177,7 +171,7 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
             }
         }
         __syncwarp();
-        const uint32_t tile_tx = stage_bytes;
+        const uint32_t tile_tx = (uint32_t)a.Bp * 128u;
         uint32_t n = 0;
         for (int t = 0; t < a.T; t++)
             for (int g = 0; g < NG; g++) {
@@ -194,7 +188,7 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                         mbar_wait(empty_bar(s), ((n / RST) & 1) ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(full_bar(s), tile_tx);
-                            tma_load_2d(ring0 + s * stage_bytes, hl ? &mapMlo : &mapMhi, full_bar(s), (int)rank * Kc + kb * 64, row);
+                            tma_load_2d(ring0 + s * TILE_BYTES, hl ? &mapMlo : &mapMhi, full_bar(s), (int)rank * Kc + kb * 64, row);
                         }
                         __syncwarp();
                     }
@@ -219,7 +213,7 @@ lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                         if (kb == 0 && hl == 0 && mw == 0 && lane == 0) TRACE4(2);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t ad = make_sw128_desc(ring0 + s * stage_bytes);
+                            const uint64_t ad = make_sw128_desc(ring0 + s * TILE_BYTES);
                             const uint64_t bh = make_sw128_desc(whi0 + kb * WT), bl = make_sw128_desc(wlo0 + kb * WT);
 #pragma unroll
                             for (int ks = mw; ks < 4; ks += MMAW) {
