@@ -44,7 +44,10 @@ struct AprilASRModel_i;
 struct SyncReq {                                 // one blocked aas_feed_pcm16 / aas_flush call of a synchronous session
     AprilASRSession_i* s = nullptr;
     PassItem item;
-    bool done = false;
+    // 0 = queued, 1 = "you lead the next pass", 2 = done. Every caller sleeps on ITS OWN word (C++20 atomic wait = one futex per
+    // request): measured with one shared mutex + condition variable, 256 callers woken by a finished pass needed 1-5 ms to get
+    // through the mutex one by one, which spread the next tick's arrivals over two passes.
+    std::atomic<int> state{ 0 };
 };
 
 // One GPU of a model: the engine (weights replicated per device) plus the two things that build batched passes
@@ -61,7 +64,7 @@ struct Lane {
     std::mutex qmu;
     std::condition_variable qcv;
     std::vector<SyncReq*> queue;
-    bool leader_active = false;
+    bool leader_active = false, leader_in_window = false;
     int live_sync = 0;                           // synchronous sessions placed on this lane
     int miss_streak = 0;                         // consecutive windows that caught nobody
     long last_pass_us = 0;                       // smoothed duration of this lane's coalesced passes
@@ -143,53 +146,67 @@ static void run_items(std::vector<AprilASRSession_i*>& ss, std::vector<PassItem>
 
 // ---------------------------------------------------------------------------------------------
 // synchronous call -> one request in the lane's queue; returns after this session's callbacks have run on this thread
+enum { REQ_QUEUED = 0, REQ_LEAD = 1, REQ_DONE = 2 };
+
+static void lead_one_pass(Lane& L) {
+    std::unique_lock<std::mutex> lk(L.qmu);
+    // Coalescing window: wait while callers keep arriving — until every live synchronous session of this GPU has a call queued,
+    // or nobody new came for a quiet interval, or the cap is reached. The interval scales with what a pass costs (an eighth of
+    // the last pass, at least `coalesce_us`): the threads released by one 40 ms audio tick arrive in bursts over a few hundred
+    // microseconds, and one more pass for the stragglers costs far more than waiting for them; a lone caller among many idle
+    // sessions pays one interval.
+    const long win = L.model->coalesce_us;
+    if (win > 0 && (int)L.queue.size() < L.live_sync && L.miss_streak < 4) {
+        const long quiet = std::max(win, L.last_pass_us / 8), cap_us = std::max(10 * win, L.last_pass_us / 2);
+        const auto cap = std::chrono::steady_clock::now() + std::chrono::microseconds(cap_us);
+        L.leader_in_window = true;
+        for (;;) {
+            const size_t seen = L.queue.size();
+            if ((int)seen >= L.live_sync) break;
+            const auto now = std::chrono::steady_clock::now();
+            if (now >= cap) break;
+            L.qcv.wait_until(lk, std::min(cap, now + std::chrono::microseconds(quiet)));
+            if (L.queue.size() == seen && std::chrono::steady_clock::now() >= now + std::chrono::microseconds(quiet)) break;   // a quiet interval
+        }
+        L.leader_in_window = false;
+    }
+    std::vector<SyncReq*> batch;
+    batch.swap(L.queue);
+    L.miss_streak = batch.size() > 1 ? 0 : std::min(L.miss_streak + 1, 1000);
+    if (L.miss_streak >= 4 && (L.miss_streak & 63) == 0) L.miss_streak = 0;        // probe again now and then
+    lk.unlock();
+    std::vector<PassItem> items(batch.size());
+    for (size_t i = 0; i < batch.size(); i++) items[i] = std::move(batch[i]->item);
+    const auto p0 = std::chrono::steady_clock::now();
+    L.engine->run_pass(items);
+    const long pass_us = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - p0).count();
+    for (size_t i = 0; i < batch.size(); i++) batch[i]->item = std::move(items[i]);
+    lk.lock();
+    L.last_pass_us = (3 * L.last_pass_us + pass_us) / 4;
+    SyncReq* next = L.queue.empty() ? nullptr : L.queue.front();     // calls that queued up during the pass: the first of them leads the next one
+    if (!next) L.leader_active = false;
+    lk.unlock();
+    if (next) { next->state.store(REQ_LEAD, std::memory_order_release); next->state.notify_one(); }
+    for (auto* b : batch) { b->state.store(REQ_DONE, std::memory_order_release); b->state.notify_one(); }   // after this store the request may be gone
+}
+
 static void sync_submit(AprilASRSession_i* s, const int16_t* pcm, size_t count, bool flush) {
     Lane& L = *s->lane;
     SyncReq r;
     r.s = s;
     r.item.fr = &s->fr; r.item.cookie = s; r.item.pcm = pcm; r.item.count = count; r.item.flush = flush;
-    std::unique_lock<std::mutex> lk(L.qmu);
-    L.queue.push_back(&r);
-    if (L.leader_active) L.qcv.notify_all();                 // a leader inside its window may now have everybody
-    while (!r.done) {
-        if (L.leader_active) { L.qcv.wait(lk); continue; }
-        L.leader_active = true;                              // I lead: my request is in the queue, so it is part of my batch
-        // Coalescing window: wait while callers keep arriving — until every live synchronous session of this GPU has a call queued,
-        // or nobody new came for a quiet interval, or the cap is reached. The interval scales with what a pass costs (an eighth of
-        // the last pass, at least `coalesce_us`): 256 threads released by the same 40 ms audio tick arrive over a few hundred
-        // microseconds in bursts, and one more pass for the stragglers costs far more than waiting for them; a lone caller among
-        // many idle sessions pays one interval.
-        const long win = L.model->coalesce_us;
-        if (win > 0 && (int)L.queue.size() < L.live_sync && L.miss_streak < 4) {
-            const long quiet = std::max(win, L.last_pass_us / 8), cap_us = std::max(10 * win, L.last_pass_us / 2);
-            const auto cap = std::chrono::steady_clock::now() + std::chrono::microseconds(cap_us);
-            for (;;) {
-                const size_t seen = L.queue.size();
-                if ((int)seen >= L.live_sync) break;
-                const auto now = std::chrono::steady_clock::now();
-                if (now >= cap) break;
-                L.qcv.wait_until(lk, std::min(cap, now + std::chrono::microseconds(quiet)));
-                if (L.queue.size() == seen && std::chrono::steady_clock::now() >= now + std::chrono::microseconds(quiet)) break;   // a quiet interval
-            }
-        }
-        std::vector<SyncReq*> batch;
-        batch.swap(L.queue);
-        L.miss_streak = batch.size() > 1 ? 0 : std::min(L.miss_streak + 1, 1000);
-        if (L.miss_streak >= 4 && (L.miss_streak & 63) == 0) L.miss_streak = 0;        // probe again now and then
-        lk.unlock();
-        std::vector<PassItem> items(batch.size());
-        for (size_t i = 0; i < batch.size(); i++) items[i] = std::move(batch[i]->item);
-        const auto p0 = std::chrono::steady_clock::now();
-        L.engine->run_pass(items);
-        const long pass_us = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - p0).count();
-        for (size_t i = 0; i < batch.size(); i++) batch[i]->item = std::move(items[i]);
-        lk.lock();
-        L.last_pass_us = (3 * L.last_pass_us + pass_us) / 4;
-        for (auto* b : batch) b->done = true;
-        L.leader_active = false;
-        L.qcv.notify_all();                                  // wakes my batch (done) and, if calls queued up meanwhile, the next leader
+    {
+        std::lock_guard<std::mutex> lk(L.qmu);
+        L.queue.push_back(&r);
+        if (!L.leader_active) { L.leader_active = true; r.state.store(REQ_LEAD, std::memory_order_relaxed); }
+        else if (L.leader_in_window) L.qcv.notify_one();     // only a leader inside its window sleeps on the condition variable
     }
-    lk.unlock();
+    for (;;) {
+        const int st = r.state.load(std::memory_order_acquire);
+        if (st == REQ_DONE) break;
+        if (st == REQ_LEAD) { lead_one_pass(L); continue; }  // my own request is in the batch I run (it was queued before I became leader)
+        r.state.wait(REQ_QUEUED, std::memory_order_acquire);
+    }
     replay(s, r.item, flush);
 }
 

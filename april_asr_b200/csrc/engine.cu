@@ -16,7 +16,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_scan4.cuh"
 #include "kernels_scan3.cuh"
-#include "kernels_greedy_tc.cuh"
+#include "kernels_scan5.cuh"
 
 namespace april {
 
@@ -190,12 +190,14 @@ public:
     std::vector<TcLayer> tlayers;
     bool gemm_attr[16] = {};
     // wide-batch scan (kernels_scan4.cuh): sessions on the UMMA M dimension, K split over clusters of scan4_cs CTAs
-    struct Scan4Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; __half* w3 = nullptr; CUtensorMap mapW3; };   // w3: the same W_eff in the small-batch kernel's layout
+    struct Scan4Layer { __half* w = nullptr; float inv = 1.f; CUtensorMap mapW; TcWeight w_hr; __half* w3 = nullptr; CUtensorMap mapW3; __half* w5 = nullptr; CUtensorMap mapW5; };   // w3 / w5: the same W_eff in the small-batch / pair kernel's layout
     std::vector<Scan4Layer> s4layers;
     bool scan4 = false;
     int scan4_cs = 2, scan4_mmaw = 2;
     size_t scan4_smem = 0;
     bool scan3 = false;             // small-batch kernel (kernels_scan3.cuh) available: used for passes of <= 64 sessions
+    bool scan5 = false;             // pair kernel (kernels_scan5.cuh) available: used for passes of > 128 sessions
+    size_t scan5_smem = 0;
     size_t scan3_smem = 0;
     size_t mall_rows = 0;           // rows per m plane of the current pass chunking: (Tc + 1) * B
     float* m_store = nullptr;       // [slot][L][H]
@@ -209,12 +211,6 @@ public:
     float* dout_blank = nullptr;
     float* dtab = nullptr;            // decoder output table [V][V][J] (fast greedy path)
     bool fast_greedy = false;
-    // tensor-core joiner + search (kernels_greedy_tc.cuh): joiner rows as fp16 (hi, lo) per cluster rank
-    bool greedy_tc = false;
-    __half* gt_w = nullptr;
-    float gt_inv = 1.f;
-    CUtensorMap gt_mapW;
-    size_t gt_smem = 0;
     int gr_R = 0;
     size_t gr_smem = 0;
     int frame_N = 0, frame_shift = 0;
@@ -409,30 +405,6 @@ public:
         CK(cudaFree(Y));
         CK(cudaFuncSetAttribute(k::greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gr_smem));
         fast_greedy = true;
-        init_greedy_tc();
-    }
-
-    // the tensor-core search needs the decoder table (above), V <= 8 x 64 vocabulary rows and J in whole 64-wide k-blocks
-    void init_greedy_tc() {
-        const int V = d.V, J = d.J;
-        const char* sel = getenv("APRIL_B200_GREEDY");
-        if (npass == 0 || !(sel && !strcmp(sel, "tc")) || V > gt::CLUSTER * gt::RV || J % 64 != 0 || J > 512) return;   // opt-in until validated on hardware
-        gt_smem = gt::smem_bytes(J, V);
-        if (gt_smem > 227 * 1024) return;
-        if (cudaFuncSetAttribute(gt::joiner_greedy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem) != cudaSuccess) { cudaGetLastError(); return; }
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(gt::CLUSTER); cfg.blockDim = dim3(gt::THREADS); cfg.dynamicSmemBytes = gt_smem; cfg.stream = st;
-        int ncl = 0;
-        if (cudaOccupancyMaxActiveClusters(&ncl, gt::joiner_greedy_tc_kernel, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return; }
-        std::vector<float> jw((size_t)V * J);
-        CK(cudaMemcpy(jw.data(), jp.join_w, sizeof(float) * jw.size(), cudaMemcpyDeviceToHost));
-        const float sc = pow2_scale(jw, gt_inv);
-        CK(cudaMalloc(&gt_w, sizeof(__half) * (size_t)gt::CLUSTER * 2 * gt::RV * J)); owned.push_back(gt_w);
-        gt::pack_joiner_kernel<<<dim3(gt::CLUSTER, gt::RV), 128, 0, st>>>(jp.join_w, gt_w, V, J, sc);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));
-        gt_mapW = make_map_2d(gt_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)gt::CLUSTER * 2 * gt::RV, (uint64_t)J, 64, gt::RV, true);
-        greedy_tc = true;
     }
 
     size_t conv_smem() const {
@@ -597,6 +569,22 @@ public:
             }
             cudaGetLastError();
         }
+        {   // the pair kernel: clusters of 4, all co-resident
+            static const bool off = !(getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "pair"));   // opt-in until validated on hardware
+            scan5_smem = scan5::smem_bytes(H);
+            scan5 = !off && H % 128 == 0 && GC % scan5::CL == 0 && scan5_smem <= 227 * 1024 &&
+                    cudaFuncSetAttribute(scan5::lstm_scan5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan5_smem) == cudaSuccess;
+            if (scan5) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan5::THREADS); cfg.dynamicSmemBytes = scan5_smem; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = scan5::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, scan5::lstm_scan5_kernel, &cfg) != cudaSuccess || ncl * scan5::CL < GC) scan5 = false;
+            }
+            cudaGetLastError();
+        }
         const int CS = scan4_cs, NC = 32 * CS, Kc = H / CS;
         float *dA = nullptr, *dB = nullptr, *dC = nullptr;
         CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
@@ -622,6 +610,13 @@ public:
                 CK(cudaGetLastError());
                 CK(cudaStreamSynchronize(st));
                 sl.mapW3 = make_map_2d(sl.w3, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 128, (uint64_t)(H / 2), 64, 128, true);
+            }
+            if (scan5) {
+                CK(cudaMalloc(&sl.w5, sizeof(__half) * (size_t)GC * 2 * scan5::NB * (H / 2))); owned.push_back(sl.w5);
+                scan5::pack_weff5_kernel<<<dim3((unsigned)GC, scan5::NB), 128, 0, st>>>(dC, sl.w5, H, sc);
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(st));
+                sl.mapW5 = make_map_2d(sl.w5, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)GC * 2 * scan5::NB, (uint64_t)(H / 2), 64, scan5::NB, true);
             }
             s4layers.push_back(sl);
         }
@@ -661,6 +656,38 @@ public:
         if (do_trace) dump_trace(a.GC, tc, a.GC / 2);
     }
 
+    // large batches (> 128 sessions): items of <= 256 sessions through the pair kernel, two items per launch
+    void scan5_layer(const Scan4Layer& sl, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B, __half* Mh, __half* Ml, int l) {
+        const int H = d.H;
+        const int per_launch = scan5::MAXI * scan5::ITEM;
+        for (int g0 = 0; g0 < B; g0 += per_launch) {
+            const int Bc = std::min(per_launch, B - g0);
+            scan4::Args a{};
+            a.T = tc; a.t0 = t0;
+            a.NG = (Bc + scan5::ITEM - 1) / scan5::ITEM;
+            const int per = ((Bc + a.NG - 1) / a.NG + 7) & ~7;
+            for (int g = 0, o = 0; g < scan4::MAXG; g++) { a.goff[g] = o; a.Bg[g] = g < a.NG ? std::max(0, std::min(per, Bc - o)) : 0; o += a.Bg[g]; }
+            a.Bp = scan5::HALF;
+            a.Bs = B; a.g0 = g0; a.H = H; a.GC = H / scan4::UNITS;
+            a.inv_scale = sl.inv; a.nsteps = d_nsteps; a.G = G; a.c_state = cw; a.m_state = mw;
+            a.Mx_hi = Mh; a.Mx_lo = Ml; a.counter = scan_counters;
+            static const bool want_trace = getenv("APRIL_B200_SCAN_TRACE") != nullptr;
+            const bool do_trace = want_trace && l == 0 && g0 == 0 && tc >= 64;
+            if (do_trace) { b_trace.ensure(sizeof(unsigned long long) * (size_t)a.GC * tc * 8); CK(cudaMemsetAsync(b_trace.p, 0, sizeof(unsigned long long) * (size_t)a.GC * tc * 8, st)); a.trace = b_trace.as<unsigned long long>(); }
+            CK(cudaMemsetAsync(scan_counters, 0, 256 * sizeof(unsigned), st));
+            const CUtensorMap mh = make_map_f16(Mh, (uint64_t)(tc + 1) * B, (uint64_t)H, scan5::HALF), ml = make_map_f16(Ml, (uint64_t)(tc + 1) * B, (uint64_t)H, scan5::HALF);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan5::THREADS); cfg.dynamicSmemBytes = scan5_smem; cfg.stream = st;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = scan5::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+            cfg.attrs = at; cfg.numAttrs = capturing ? 1 : 2;
+            CK(cudaLaunchKernelEx(&cfg, scan5::lstm_scan5_kernel, sl.mapW5, mh, ml, a));
+            launch_check();
+            if (do_trace) dump_trace(a.GC, tc, 2);
+        }
+    }
+
     // one layer, steps [t0, t0+tc) of all B sessions of the pass: up to 512 sessions (4 groups of <= 128) per launch
     void scan4_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int H = d.H;
@@ -670,6 +697,7 @@ public:
         const size_t n0 = (size_t)B * H;
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
         if (scan3 && B <= 64) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); return; }
+        if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
         const int per_launch = scan4::MAXG * scan4::GROUP;
         for (int g0 = 0; g0 < B; g0 += per_launch) {
@@ -1043,26 +1071,7 @@ public:
                 else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
                 span_begin(2);
-                if (greedy_tc) {
-                    const int maxc = std::max(1, num_sms / gt::CLUSTER);
-                    gt::Args ga{};
-                    ga.J = J; ga.V = d.V; ga.blank = prm.blank_id; ga.B = B; ga.Tcap = Tmax; ga.t_base = t0; ga.chunk_T = tc; ga.stride_ms = stride_ms(); ga.last_chunk = last;
-                    ga.S = std::min(gt::MAX_S, std::max(1, (B + maxc - 1) / maxc));
-                    ga.inv_scale = gt_inv; ga.bias = jp.join_b; ga.vflags = jp.vflags; ga.dtab = dtab; ga.enc_out = EO; ga.nsteps = d_nsteps; ga.slot = d_slot; ga.flush_flag = d_flush;
-                    ga.gstate = gstate; ga.rec = b_rec.as<k::DecisionRecord>(); ga.npass = b_np.as<int>(); ga.tap_logits = want_tap ? b_tap.as<float>() : nullptr;
-                    const int ncl = (B + ga.S - 1) / ga.S;
-                    static const bool gt_trace = getenv("APRIL_B200_GREEDY_TRACE") != nullptr;
-                    if (gt_trace) { ga.trace_cap = 512; b_trace.ensure(8 * 8 * 512); CK(cudaMemsetAsync(b_trace.p, 0, 8 * 8 * 512, st)); ga.trace = b_trace.as<unsigned long long>(); }
-                    gt::joiner_greedy_tc_kernel<<<ncl * gt::CLUSTER, gt::THREADS, gt_smem, st>>>(gt_mapW, ga);
-                    if (gt_trace) {
-                        std::vector<unsigned long long> h(8 * 512);
-                        CK(cudaStreamSynchronize(st));
-                        CK(cudaMemcpy(h.data(), b_trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
-                        double acc[8] = { 0 }; int n = 0; double per = 0;
-                        for (int p = 50; p < 450; p++) { if (!h[(size_t)p * 8] || !h[(size_t)(p + 1) * 8]) continue; for (int k2 = 0; k2 < 8; k2++) acc[k2] += (double)h[(size_t)p * 8 + k2] - (double)h[(size_t)p * 8]; per += (double)h[(size_t)(p + 1) * 8] - (double)h[(size_t)p * 8]; n++; }
-                        if (n) { fprintf(stderr, "greedy trace (ns from pass start, avg of %d passes; pass = %.0f ns): ", n, per / n); for (int k2 = 0; k2 < 8; k2++) fprintf(stderr, "%d:%.0f ", k2, acc[k2] / n); fprintf(stderr, "\n"); }
-                    }
-                } else if (fast_greedy) {
+                if (fast_greedy) {
                     const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
                     const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));
                     const int ncl = (B + S - 1) / S;

@@ -493,7 +493,7 @@ static void eval_node(const Node* nd, T* vals) {
 /* ------------------------------------------------------------------------------------------ */
 /* OrtApi                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
-static FakeOrtTap g_tap = NULL; static void* g_tap_ud = NULL;
+static __thread FakeOrtTap g_tap = NULL; static __thread void* g_tap_ud = NULL;   /* per calling thread: synchronous sessions Run on their caller's thread, so concurrent test threads can each tap their own session */
 static _Atomic uint64_t g_run_counts[3];
 void fake_ort_set_tap(FakeOrtTap tap, void* ud) { g_tap = tap; g_tap_ud = ud; }
 void fake_ort_get_run_counts(uint64_t c[3]) { for (int i = 0; i < 3; i++) c[i] = atomic_load(&g_run_counts[i]); }

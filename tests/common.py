@@ -156,3 +156,63 @@ def callback_diff(got, want):
     differing = sum(max(i2 - i1, j2 - j1) for tag, i1, i2, j1, j2 in sm.get_opcodes() if tag != "equal")
     fin = lambda c: [k for k in c.keys() if k[0] == 2]
     return differing, fin(got) == fin(want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Near-ties. Two fp32-grade implementations of an 84 M-parameter recurrent network agree on raw joiner logits to ~1e-4 (measured:
+# tools/precision_study.py), not to the last bit, and the greedy rules (april_session.c:306-429) threshold raw logits. A decision whose
+# margin is smaller than that difference can fall either way, and once an EMITTED token differs the two decoders sit in different
+# contexts (with random weights they do not re-converge before the next 2.2 s silence reset), so everything after it is incomparable.
+# The tests therefore require, per stream: an identical callback log, OR a divergence that starts at a decision the ORACLE's own
+# logits put within NEAR_TIE of one of the thresholds, with identical callbacks and logits within tolerance before it. Such streams
+# are counted, printed and bounded.
+# ---------------------------------------------------------------------------------------------------------------------------
+NEAR_TIE = 1e-3          # 7x the measured logit difference, half the stated 2e-3 tolerance
+
+
+def explain_difference(model_file, pcm, chunk=None, blank=0, logit_tol=2e-3):
+    """Runs one stream through both paths WITH taps (the oracle's tap is per calling thread) and locates the first diverging decision."""
+    o = run_oracle(model_file, pcm, chunk=chunk, tap=True)
+    p = run_product_batch(model_file, [pcm], chunk=chunk, tap=True)[0]
+    ok, pk = o.keys(), p.keys()
+    first_cb = next((j for j, (x, y) in enumerate(zip(pk, ok)) if x != y), None)
+    if first_cb is None and len(ok) != len(pk):
+        first_cb = min(len(ok), len(pk))
+    n = min(len(o.logits), len(p.logits))
+    gross = next((i for i in range(n) if float(np.abs(o.logits[i] - p.logits[i]).max()) > 1e-2), None)
+    upto = gross if gross is not None else n
+    err_before = max([float(np.abs(o.logits[i] - p.logits[i]).max()) for i in range(upto)] or [0.0])
+    out = {"identical": first_cb is None, "first_differing_callback": first_cb, "callbacks": len(ok), "first_diverging_pass": gross,
+           "logit_err_before": err_before, "near_tie": False, "margin": None, "tentative_only": False}
+    if first_cb is None:
+        return out
+    if gross is None:
+        # no state-changing decision differs: a tentative token (pushed, reported, popped: april_session.c:417-422) at a near-tie of its
+        # own threshold, visible in one partial only
+        nd, fin = callback_diff(p, o)
+        out["tentative_only"] = fin and nd <= 2 and len(o.logits) == len(p.logits)
+        out["near_tie"] = out["tentative_only"] and err_before < logit_tol
+        return out
+    j = max(gross - 1, 0)                                     # the decision taken on pass j changed what pass j + 1 computes
+    lo = o.logits[j]
+    nb = np.delete(lo, blank)
+    top2 = np.sort(nb)[-2:]
+    d = float(lo[blank] - top2[1])
+    margin = min(abs(d), abs(d - 1.0), abs(d - 3.5), float(top2[1] - top2[0]))
+    out["margin"] = margin
+    out["near_tie"] = margin < NEAR_TIE and err_before < logit_tol
+    return out
+
+
+def check_streams(model_file, pcms, got, want, ids, what, chunk=None, max_near_ties=2):
+    """got / want: lists of Collected indexed like `ids` (positions into got, streams of want). Asserts the policy above."""
+    bad = [(k, i) for k, i in enumerate(ids) if got[i].keys() != want[k].keys()]
+    notes = []
+    for k, i in bad:
+        ex = explain_difference(model_file, pcms[i], chunk=chunk)
+        notes.append((i, ex))
+        assert ex["near_tie"], "%s: stream at position %d differs from the oracle and it is NOT a near-tie: %s" % (what, i, ex)
+    print("%s: %d of %d checked streams identical to the oracle; verified near-ties: %s" % (
+        what, len(ids) - len(bad), len(ids), [(i, "tentative" if e["tentative_only"] else "margin %.2e at pass %d" % (e["margin"], e["first_diverging_pass"] - 1)) for i, e in notes]))
+    assert len(bad) <= max_near_ties, "%s: %d streams diverge (near-ties, but more than expected)" % (what, len(bad))
+    return len(bad)
