@@ -395,11 +395,13 @@ public:
         const size_t tab_bytes = sizeof(float) * (size_t)V * V * J;
         if (J % 32 != 0 || J / 32 > k::GC_MAX_JPL || J > 512 || gr_R > 8 * k::GC_RPW || gr_smem > 200 * 1024 || tab_bytes > ((size_t)3 << 30)) return;
         CK(cudaMalloc(&dtab, tab_bytes));
+        const int CH = std::max(1, std::min(V, 32768 / std::max(V, 1)));   // contexts per launch: ~32 K table rows at a time
         float* Y = nullptr;
-        CK(cudaMalloc(&Y, sizeof(float) * (size_t)V * d.E));
-        for (int c0 = 0; c0 < V; c0++) {
-            k::decoder_table_y_kernel<<<V, 128, 0, st>>>(jp, c0, Y);
-            gemm_launch(k::EPI_BIAS, Y, jp.dec_w, jp.dec_b, nullptr, dtab + (size_t)c0 * V * J, V, J, d.E);
+        CK(cudaMalloc(&Y, sizeof(float) * (size_t)CH * V * d.E));
+        for (int c0 = 0; c0 < V; c0 += CH) {
+            const int n = std::min(CH, V - c0);
+            k::decoder_table_y_kernel<<<dim3((unsigned)V, (unsigned)n), 128, 0, st>>>(jp, c0, Y);
+            gemm_launch(k::EPI_BIAS, Y, jp.dec_w, jp.dec_b, nullptr, dtab + (size_t)c0 * V * J, n * V, J, d.E);
         }
         CK(cudaStreamSynchronize(st));
         CK(cudaFree(Y));

@@ -1022,14 +1022,14 @@ greedy_cluster_kernel(JoinerParams P, const float* __restrict__ dtab, const floa
     cluster_sync_all();                                                       // no CTA may exit while peers can still write its inbox
 }
 
-// decoder table rows for context (c0, *): Y[c1][e] = relu(emb[c0][e] k[e][0] + emb[c1][e] k[e][1])
-__global__ void decoder_table_y_kernel(JoinerParams P, int c0, float* __restrict__ Y) {
-    const int c1 = blockIdx.x;
+// decoder table rows for contexts (c0_base + blockIdx.y, *): Y[(y * V + c1)][e] = relu(emb[c0][e] k[e][0] + emb[c1][e] k[e][1])
+__global__ void decoder_table_y_kernel(JoinerParams P, int c0_base, float* __restrict__ Y) {
+    const int c1 = blockIdx.x, c0 = c0_base + blockIdx.y;
     for (int e = threadIdx.x; e < P.E; e += blockDim.x) {
         float s = 0.f;
         s = fmaf(P.emb[(size_t)c0 * P.E + e], P.dec_conv[e * 2 + 0], s);
         s = fmaf(P.emb[(size_t)c1 * P.E + e], P.dec_conv[e * 2 + 1], s);
-        Y[(size_t)c1 * P.E + e] = fmaxf(s, 0.f);
+        Y[((size_t)blockIdx.y * P.V + c1) * P.E + e] = fmaxf(s, 0.f);
     }
 }
 
