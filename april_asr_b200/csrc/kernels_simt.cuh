@@ -656,6 +656,7 @@ __device__ bool greedy_decide(GreedyState& st, const uint8_t* vf, int blank, flo
         if ((lf & VF_DIGIT) && (f & VF_DOT)) { is_eos = false; is_punct = false; }   // "10.5" is not a sentence end
     }
     if (!was_context_cleared && is_punct && !is_equal_to_previous && max_val > (blank_val - 3.5f)) is_blank = false;   // :356-358
+    if (max_idx < 0) is_blank = true;                                        // all non-blank logits non-finite: emit nothing (mirrored in session.cpp)
     if (!is_blank) {
         st.last_emission_ms = st.current_ms;                                 // :362
         st.ctx0 = st.ctx1; st.ctx1 = max_idx; ctx_changed = true;            // :364 aas_update_context

@@ -87,6 +87,7 @@ bool TokenShaper::on_joiner_pass(float early_emit, int max_idx, float max_val, f
     if (is_end_of_sentence) flags |= APRIL_TOKEN_FLAG_SENTENCE_END_BIT;
     token.flags = (AprilTokenFlagBits)flags;
     if (!was_context_cleared && is_punctuation && !is_equal_to_previous && max_val > (blank_val - 3.5f)) is_blank = false;   // :356-358
+    if (max_idx < 0) is_blank = true;        // no finite non-blank logit (non-finite activations): nothing can be emitted; the reference would index tokens[-1]
 
     if (!is_blank) {
         last_emission_time_ms_ = current_time_ms_;

@@ -188,7 +188,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=None, help="wall seconds of one CPU sample (default: 20 s inside the b200 arm; 150 s / (steps + warmup) in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the b512 and stream blocks")
-    ap.add_argument("--mode", default="bulk", choices=["bulk", "stream"], help="stream = only BASELINE configs[3] (256 sessions x 40 ms chunks via aas_feed_pcm16)")
+    ap.add_argument("--mode", default="bulk", choices=["bulk", "stream", "soak"], help="stream = only BASELINE configs[3] (256 sessions x 40 ms chunks via aas_feed_pcm16); soak = BASELINE configs[4] per GPU: long-form streams fed in many calls (state carried across all of them)")
+    ap.add_argument("--soak-minutes", type=float, default=60.0, help="audio minutes per session in --mode soak")
+    ap.add_argument("--soak-chunk", type=float, default=10.0, help="audio seconds per feed call in --mode soak")
     ap.add_argument("--ticks", type=int, default=250)
     a = ap.parse_args()
 
@@ -344,6 +346,47 @@ def main():
             print(json.dumps({"metric": "chunk_latency_ms", "value": sb["latency_ms"]["p50"], "unit": "ms", "n_gpus": world, "steps": a.ticks, "warmup": 20, "higher_is_better": False,
                               "ms_per_step": sb["tick_ms"]["p50"], "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": sb["workload"]}, "stream": sb}))
         m.close()
+        return
+
+    if a.mode == "soak":
+        # BASELINE configs[4]: 128 x 1 h over 8 GPUs = 16 long-form sessions per GPU. Each session loops a 60 s synthetic clip; every
+        # feed call advances all sessions by --soak-chunk seconds, so LSTM state, feature carry and greedy context survive
+        # minutes * 60 / chunk passes. Throughput = frames over the device time of all passes (max over ranks).
+        S = a.sessions if a.sessions != 64 else 16
+        clip = gen_streams(dist_util.shard_stream_ids(rank, world, S), 16000 * 60)
+        nchunk = int(16000 * a.soak_chunk)
+        calls = int(a.soak_minutes * 60 / a.soak_chunk)
+        counters = (ctypes.c_uint64 * 4)()
+        ss = []
+        for _ in range(S):
+            cfg = A.AprilConfig(); cfg.handler = handler; cfg.userdata = ctypes.cast(counters, ctypes.c_void_p); cfg.flags = 0
+            ss.append(lib.c.aas_create_session(m.handle, cfg))
+        arr = (ctypes.c_void_p * S)(*ss)
+        cnts = (ctypes.c_size_t * S)(*([nchunk] * S))
+        st = _ffi.AprilB200Stats()
+        lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(calls):
+            off = (k * nchunk) % (16000 * 60 - nchunk)
+            ptrs = (ctypes.POINTER(ctypes.c_short) * S)(*[ctypes.cast(p.ctypes.data + 2 * off, ctypes.POINTER(ctypes.c_short)) for p in clip])
+            assert lib.c.aab_feed_pcm16_batch(arr, ptrs, cnts, S) == 0
+        assert lib.c.aab_flush_batch(arr, S) == 0
+        wall = time.perf_counter() - t0
+        lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
+        for h in ss:
+            lib.c.aas_free(h)
+        (wall_s, dev_s), (frames,) = dist_util.combine(dist, "cuda", [wall, st.device_ms / 1e3], [st.frames])
+        if rank == 0:
+            print(json.dumps({"metric": "audio_frames_per_sec", "mode": "soak", "value": frames / dev_s, "unit": "frames/s", "n_gpus": world, "steps": calls, "warmup": 0,
+                              "ms_per_step": 1e3 * dev_s / calls, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": "%d long-form sessions per GPU x %.0f min, %.0f s per feed call (%d calls + flush), state carried across all calls (BASELINE configs[4] per GPU)" % (S, a.soak_minutes, a.soak_chunk, calls)},
+                              "x_realtime_per_stream": a.soak_minutes * 60 / dev_s, "e2e": {"value": frames / wall_s, "unit": "frames/s", "x_realtime_per_stream": a.soak_minutes * 60 / wall_s},
+                              "results": {"encoder_steps": int(st.encoder_steps), "final_tokens": int(counters[3]), "final_callbacks": int(counters[1]), "silence_callbacks": int(counters[2])}}))
+        m.close()
+        if dist is not None:
+            dist.destroy_process_group()
         return
 
     r = run_bulk(a.sessions, a.seconds, a.warmup, a.steps, dist_util.shard_stream_ids(rank, world, a.sessions))
