@@ -708,7 +708,8 @@ public:
         __half *Mh = b_mall.as<__half>(), *Ml = Mh + plane;
         const size_t n0 = (size_t)B * H;
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
-        if (scan3 && B <= 64) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); return; }
+        static const bool no_small = getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "nosmall");   // dev: scan4 for every size
+        if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); if (l == 0 && t0 == 0) dump_m_planes(Mh, tc, B); return; }
         if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); if (l == 0 && t0 == 0) dump_m_planes(Mh, tc, B); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
         const int per_launch = scan4::MAXG * scan4::GROUP;

@@ -5,14 +5,14 @@ import argparse, os, subprocess, sys, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
-ap = argparse.ArgumentParser(); ap.add_argument("--model", default="mid"); ap.add_argument("--sessions", type=int, default=150); ap.add_argument("--seconds", type=float, default=2.0); ap.add_argument("--child", default=None)
+ap = argparse.ArgumentParser(); ap.add_argument("--model", default="mid"); ap.add_argument("--sessions", type=int, default=150); ap.add_argument("--seconds", type=float, default=2.0); ap.add_argument("--a", default=""); ap.add_argument("--b", default="APRIL_B200_SCAN=pair"); ap.add_argument("--child", default=None)
 a = ap.parse_args()
 if a.child:
     import common as C
     C.run_product_batch(C.model_path(a.model), [C.gen_stream(700 + i, int(16000 * a.seconds)) for i in range(a.sessions)], flush=False)
     sys.exit(0)
 out = {}
-for arm, env in (("scan4", {}), ("pair", {"APRIL_B200_SCAN": "pair"})):
+for arm, env in (("scan4", dict(kv.split("=", 1) for kv in a.a.split())), ("pair", dict(kv.split("=", 1) for kv in a.b.split()))):
     f = tempfile.mktemp(suffix=".bin")
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--model", a.model, "--sessions", str(a.sessions), "--seconds", str(a.seconds), "--child", "1"],
                        env=dict(os.environ, APRIL_B200_DUMP_M=f, **env), capture_output=True, text=True, timeout=600)
@@ -24,4 +24,5 @@ print("planes", out["scan4"].shape, "max diff", d.max())
 for t in range(min(4, d.shape[0])):
     dt = d[t]
     bad_units = np.where(dt.max(axis=0) > 1e-3)[0]; bad_sess = np.where(dt.max(axis=1) > 1e-3)[0]
-    print("row block", t, "max", dt.max(), "bad units", len(bad_units), bad_units[:40].tolist(), "bad sessions", len(bad_sess), bad_sess[:20].tolist(), "...", bad_sess[-5:].tolist())
+    print("row block", t, "max", dt.max(), "bad units", len(bad_units), bad_units[:48].tolist(), "bad sessions", len(bad_sess), bad_sess[:20].tolist(), "...", bad_sess[-5:].tolist())
+    if len(bad_units): print("   per-unit max diff (first 64 units):", np.round(dt.max(axis=0)[:64], 3).tolist())
