@@ -691,9 +691,12 @@ public:
     }
 
     // dev aid: APRIL_B200_DUMP_M=<file> writes the hi plane of layer 0's m rows of the first chunk of every pass ([(tc + 1) * B][H] fp16, raw)
+    bool dumped_once = false;
+    static int dump_layer() { static const int l = getenv("APRIL_B200_DUMP_LAYER") ? atoi(getenv("APRIL_B200_DUMP_LAYER")) : 0; return l; }
     void dump_m_planes(const __half* Mh, int tc, int B) {
         static const char* path = getenv("APRIL_B200_DUMP_M");
-        if (!path) return;
+        if (!path || dumped_once) return;
+        dumped_once = true;
         std::vector<__half> h((size_t)(tc + 1) * B * d.H);
         CK(cudaStreamSynchronize(st));
         CK(cudaMemcpy(h.data(), Mh, h.size() * sizeof(__half), cudaMemcpyDeviceToHost));
@@ -709,8 +712,8 @@ public:
         const size_t n0 = (size_t)B * H;
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
         static const bool no_small = getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "nosmall");   // dev: scan4 for every size
-        if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); if (l == 0 && t0 == 0) dump_m_planes(Mh, tc, B); return; }
-        if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); if (l == 0 && t0 == 0) dump_m_planes(Mh, tc, B); return; }
+        if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B); return; }
+        if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
         const int per_launch = scan4::MAXG * scan4::GROUP;
         for (int g0 = 0; g0 < B; g0 += per_launch) {
@@ -736,7 +739,7 @@ public:
             launch_check();
             if (do_trace) dump_trace(a.GC, tc, 1);
         }
-        if (l == 0 && t0 == 0) dump_m_planes(Mh, tc, B);
+        if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B);
     }
 
     // the radix-8 front-end serves the 512-sample window (every model of the reference: 25 ms at 16 kHz); other windows take the generic kernel

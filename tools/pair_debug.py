@@ -5,22 +5,22 @@ import argparse, os, subprocess, sys, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
-ap = argparse.ArgumentParser(); ap.add_argument("--model", default="mid"); ap.add_argument("--sessions", type=int, default=150); ap.add_argument("--seconds", type=float, default=2.0); ap.add_argument("--a", default=""); ap.add_argument("--b", default="APRIL_B200_SCAN=pair"); ap.add_argument("--child", default=None)
+ap = argparse.ArgumentParser(); ap.add_argument("--model", default="mid"); ap.add_argument("--sessions", type=int, default=150); ap.add_argument("--seconds", type=float, default=2.0); ap.add_argument("--ragged", type=int, default=0); ap.add_argument("--tap", type=int, default=0); ap.add_argument("--flush", type=int, default=0); ap.add_argument("--layer", type=int, default=0); ap.add_argument("--a", default=""); ap.add_argument("--b", default="APRIL_B200_SCAN=pair"); ap.add_argument("--child", default=None)
 a = ap.parse_args()
 if a.child:
     import common as C
-    C.run_product_batch(C.model_path(a.model), [C.gen_stream(700 + i, int(16000 * a.seconds)) for i in range(a.sessions)], flush=False)
+    C.run_product_batch(C.model_path(a.model), [C.gen_stream(700 + i, int(16000 * a.seconds) + (977 * i if a.ragged else 0)) for i in range(a.sessions)], flush=bool(a.flush), tap=bool(a.tap))
     sys.exit(0)
 out = {}
 for arm, env in (("scan4", dict(kv.split("=", 1) for kv in a.a.split())), ("pair", dict(kv.split("=", 1) for kv in a.b.split()))):
     f = tempfile.mktemp(suffix=".bin")
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--model", a.model, "--sessions", str(a.sessions), "--seconds", str(a.seconds), "--child", "1"],
-                       env=dict(os.environ, APRIL_B200_DUMP_M=f, **env), capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--model", a.model, "--sessions", str(a.sessions), "--seconds", str(a.seconds), "--ragged", str(a.ragged), "--tap", str(a.tap), "--flush", str(a.flush), "--child", "1"],
+                       env=dict(os.environ, APRIL_B200_DUMP_M=f, APRIL_B200_DUMP_LAYER=str(a.layer), **env), capture_output=True, text=True, timeout=600)
     if r.returncode != 0: print(arm, "failed", r.stderr[-500:]); sys.exit(1)
     raw = open(f, "rb").read(); hdr = np.frombuffer(raw[:16], np.int32); T1, B, H = int(hdr[0]), int(hdr[1]), int(hdr[2])
     out[arm] = np.frombuffer(raw[16:], np.float16).reshape(T1, B, H).astype(np.float32)
 d = np.abs(out["scan4"] - out["pair"])
-print("planes", out["scan4"].shape, "max diff", d.max())
+print("config", vars(a)); print("planes", out["scan4"].shape, "max diff", d.max(), "first bad row block", next((t for t in range(d.shape[0]) if d[t].max() > 1e-3), None))
 for t in range(min(4, d.shape[0])):
     dt = d[t]
     bad_units = np.where(dt.max(axis=0) > 1e-3)[0]; bad_sess = np.where(dt.max(axis=1) > 1e-3)[0]
