@@ -697,10 +697,12 @@ public:
         static const char* path = getenv("APRIL_B200_DUMP_M");
         if (!path || dumped_once) return;
         dumped_once = true;
-        std::vector<__half> h((size_t)(tc + 1) * B * d.H);
+        const size_t n = (size_t)(tc + 1) * B * d.H;
+        std::vector<__half> h(2 * n);
         CK(cudaStreamSynchronize(st));
-        CK(cudaMemcpy(h.data(), Mh, h.size() * sizeof(__half), cudaMemcpyDeviceToHost));
-        if (FILE* f = fopen(path, "wb")) { int hdr[4] = { tc + 1, B, d.H, 0 }; fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(__half), h.size(), f); fclose(f); }
+        CK(cudaMemcpy(h.data(), Mh, n * sizeof(__half), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h.data() + n, Mh + mall_rows * d.H, n * sizeof(__half), cudaMemcpyDeviceToHost));     // lo plane
+        if (FILE* f = fopen(path, "wb")) { int hdr[4] = { tc + 1, B, d.H, 2 }; fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(__half), h.size(), f); fclose(f); }
     }
 
     // one layer, steps [t0, t0+tc) of all B sessions of the pass: up to 512 sessions (4 groups of <= 128) per launch

@@ -18,9 +18,10 @@ for arm, env in (("scan4", dict(kv.split("=", 1) for kv in a.a.split())), ("pair
                        env=dict(os.environ, APRIL_B200_DUMP_M=f, APRIL_B200_DUMP_LAYER=str(a.layer), **env), capture_output=True, text=True, timeout=600)
     if r.returncode != 0: print(arm, "failed", r.stderr[-500:]); sys.exit(1)
     raw = open(f, "rb").read(); hdr = np.frombuffer(raw[:16], np.int32); T1, B, H = int(hdr[0]), int(hdr[1]), int(hdr[2])
-    out[arm] = np.frombuffer(raw[16:], np.float16).reshape(T1, B, H).astype(np.float32)
-d = np.abs(out["scan4"] - out["pair"])
-print("config", vars(a)); print("planes", out["scan4"].shape, "max diff", d.max(), "first bad row block", next((t for t in range(d.shape[0]) if d[t].max() > 1e-3), None))
+    out[arm] = np.frombuffer(raw[16:], np.float16).reshape(2, T1, B, H).astype(np.float32)
+dl = np.abs(out["scan4"][1] - out["pair"][1]); print("LO plane: max diff", dl.max(), "first bad row block (> 1e-6)", next((t for t in range(dl.shape[0]) if dl[t].max() > 1e-6), None), "max |lo|", np.abs(out["pair"][1]).max(), np.abs(out["scan4"][1]).max())
+d = np.abs(out["scan4"][0] - out["pair"][0])
+print("config", vars(a)); print("planes", out["scan4"][0].shape, "max diff", d.max(), "first bad row block", next((t for t in range(d.shape[0]) if d[t].max() > 1e-3), None))
 for t in range(min(4, d.shape[0])):
     dt = d[t]
     bad_units = np.where(dt.max(axis=0) > 1e-3)[0]; bad_sess = np.where(dt.max(axis=1) > 1e-3)[0]
