@@ -625,6 +625,47 @@ public:
         CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
         if (!scan_counters) { CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned))); owned.push_back(scan_counters); }
         scan4 = true;
+        if (getenv("APRIL_B200_VERIFY_W")) for (int l = 0; l < (int)s4layers.size() && l < 4; l++) verify_packed_weights(l, "after load");
+    }
+
+    // dev aid (APRIL_B200_VERIFY_W): the three packed copies of a layer's W_eff must hold the same numbers
+    void verify_packed_weights(int l, const char* when) {
+        const int H = d.H, GC = H / 8;
+        const Scan4Layer& sl = s4layers[(size_t)l];
+        auto fetch = [&](const __half* p, size_t n) { std::vector<__half> h(n); CK(cudaMemcpy(h.data(), p, n * sizeof(__half), cudaMemcpyDeviceToHost)); return h; };
+        std::vector<float> ref((size_t)4 * H * H, 0.f);
+        {   // scan4 layout (CS = 2): dst[((c * 2 + hl) * NC + n) * Kc + k], n = p * 32 + hc * 16 + gate * 4 + u4, unit = (c / 2) * 16 + p * 8 + hc * 4 + u4, K slice c % 2
+            const int NC = 64, Kc = H / 2;
+            auto w = fetch(sl.w, (size_t)GC * 2 * NC * Kc);
+            for (int c = 0; c < GC; c++) for (int n = 0; n < NC; n++) {
+                const int p = n >> 5, hc = (n >> 4) & 1, g4 = (n >> 2) & 3, u4 = n & 3, unit = (c / 2) * 16 + p * 8 + hc * 4 + u4, r = c % 2;
+                for (int k = 0; k < Kc; k++) ref[((size_t)g4 * H + unit) * H + (size_t)r * Kc + k] = __half2float(w[(((size_t)c * 2 + 0) * NC + n) * Kc + k]) + __half2float(w[(((size_t)c * 2 + 1) * NC + n) * Kc + k]);
+            }
+        }
+        double d3 = 0, d5 = 0;
+        if (sl.w3) {
+            const int KH = H / 2;
+            auto w = fetch(sl.w3, (size_t)GC * 128 * KH);
+            for (int c = 0; c < GC; c++) for (int rho = 0; rho < 64; rho++) {      // hi rows rho, lo rows rho + 64
+                const int half = (rho >> 5) & 1, g4 = (rho >> 3) & 3, u = rho & 7, r = c & 1, pair = c >> 1;
+                for (int k = 0; k < KH; k++) {
+                    const float v = __half2float(w[((size_t)c * 128 + rho) * KH + k]) + __half2float(w[((size_t)c * 128 + 64 + rho) * KH + k]);
+                    d3 = std::max(d3, (double)std::fabs(v - ref[((size_t)g4 * H + pair * 16 + half * 8 + u) * H + (size_t)r * KH + k]));
+                }
+            }
+        }
+        if (sl.w5) {
+            const int Kc = H / 2;
+            auto w = fetch(sl.w5, (size_t)GC * 2 * 64 * Kc);
+            for (int c = 0; c < GC; c++) for (int j = 0; j < 64; j++) {
+                const int cl = c >> 2, p = (c >> 1) & 1, q = c & 1, n = 64 * q + j, o = n >> 5, hc = (n >> 4) & 1, g4 = (n >> 2) & 3, u4 = n & 3, unit = cl * 32 + o * 8 + hc * 4 + u4;
+                for (int k = 0; k < Kc; k++) {
+                    const float v = __half2float(w[(((size_t)c * 2 + 0) * 64 + j) * Kc + k]) + __half2float(w[(((size_t)c * 2 + 1) * 64 + j) * Kc + k]);
+                    d5 = std::max(d5, (double)std::fabs(v - ref[((size_t)g4 * H + unit) * H + (size_t)p * Kc + k]));
+                }
+            }
+        }
+        fprintf(stderr, "verify W (%s) layer %d: max |scan3 - scan4| = %.3g, max |pair - scan4| = %.3g\n", when, l, d3, d5);
     }
 
     // small batches (<= 64 sessions): two interleaved groups of <= 32 sessions through the latency-optimised pair kernel
@@ -714,6 +755,8 @@ public:
         const size_t n0 = (size_t)B * H;
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
         static const bool no_small = getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "nosmall");   // dev: scan4 for every size
+        static int verify_left = getenv("APRIL_B200_VERIFY_W") ? 4 : 0;
+        if (verify_left > 0 && l < 4) { verify_left--; CK(cudaStreamSynchronize(st)); verify_packed_weights(l, "at first use"); }
         if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B); return; }
         if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
