@@ -240,7 +240,9 @@ public:
     template <class T> T* upload(const std::vector<T>& v) {
         T* p = nullptr;
         CK(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
-        if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        // on the engine's stream: `st` is non-blocking, so a copy on the legacy stream (whose DMA may still be in flight when
+        // cudaMemcpy returns from a pageable source) would not be ordered before the kernels that read the weights
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
         owned.push_back(p);
         return p;
     }
@@ -588,14 +590,14 @@ public:
             cudaGetLastError();
         }
         const int CS = scan4_cs, NC = 32 * CS, Kc = H / CS;
-        float *dA = nullptr, *dB = nullptr, *dC = nullptr;
-        CK(cudaMalloc(&dA, sizeof(float) * (size_t)4 * H * D)); CK(cudaMalloc(&dB, sizeof(float) * (size_t)D * H)); CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
+        float* dC = nullptr;
+        CK(cudaMalloc(&dC, sizeof(float) * (size_t)4 * H * H));
         std::vector<float> weff((size_t)4 * H * H);
-        for (auto& lw : w.layers) {
+        for (size_t li = 0; li < w.layers.size(); li++) {
+            const LayerWeights& lw = w.layers[li];
             Scan4Layer sl;
-            CK(cudaMemcpy(dA, lw.w_hh.data(), sizeof(float) * (size_t)4 * H * D, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(dB, lw.w_hr.data(), sizeof(float) * (size_t)D * H, cudaMemcpyHostToDevice));
-            scan4::weff_kernel<<<dim3((unsigned)((H + 15) / 16), (unsigned)((4 * H + 15) / 16)), 256, 0, st>>>(dA, dB, dC, 4 * H, H, D);
+            // W_eff = W_hh W_hr from the device copies init() uploaded on this stream
+            scan4::weff_kernel<<<dim3((unsigned)((H + 15) / 16), (unsigned)((4 * H + 15) / 16)), 256, 0, st>>>(layers[li].w_hh, layers[li].w_hr, dC, 4 * H, H, D);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(weff.data(), dC, sizeof(float) * weff.size(), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -622,7 +624,7 @@ public:
             }
             s4layers.push_back(sl);
         }
-        CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dC));
+        CK(cudaFree(dC));
         if (!scan_counters) { CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned))); owned.push_back(scan_counters); }
         scan4 = true;
         if (getenv("APRIL_B200_VERIFY_W")) for (int l = 0; l < (int)s4layers.size() && l < 4; l++) verify_packed_weights(l, "after load");
@@ -666,6 +668,29 @@ public:
             }
         }
         fprintf(stderr, "verify W (%s) layer %d: max |scan3 - scan4| = %.3g, max |pair - scan4| = %.3g\n", when, l, d3, d5);
+        // ... and TMA must deliver exactly those bytes through the layer's maps
+        auto tma_view = [&](const CUtensorMap& map, const __half* packed, size_t rows, int cols, int box_rows, const char* name) {
+            const int nkb = cols / 64; const size_t tiles = rows / box_rows * nkb, tile_bytes = (size_t)box_rows * 128;
+            uint8_t* dout = nullptr; CK(cudaMalloc(&dout, tiles * tile_bytes));
+            CK(cudaFuncSetAttribute(scan5::tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_bytes + 1024)));
+            scan5::tma_dump_kernel<<<(unsigned)tiles, 128, tile_bytes + 1024, st>>>(map, dout, box_rows, nkb);
+            CK(cudaGetLastError()); CK(cudaStreamSynchronize(st));
+            std::vector<uint8_t> img(tiles * tile_bytes); CK(cudaMemcpy(img.data(), dout, img.size(), cudaMemcpyDeviceToHost)); CK(cudaFree(dout));
+            auto h = fetch(packed, rows * cols);
+            size_t bad = 0, first = (size_t)-1;
+            for (size_t tile = 0; tile < tiles; tile++) {
+                const int kb = (int)(tile % nkb); const size_t rb = tile / nkb;
+                for (int r = 0; r < box_rows; r++) for (int c = 0; c < 8; c++) {
+                    const uint8_t* got = img.data() + tile * tile_bytes + (size_t)r * 128 + (size_t)((c ^ (r & 7)) * 16);
+                    const __half* want = h.data() + (rb * box_rows + r) * cols + kb * 64 + c * 8;
+                    if (memcmp(got, want, 16)) { bad++; if (first == (size_t)-1) first = tile; }
+                }
+            }
+            fprintf(stderr, "verify W (%s) layer %d: TMA view of the %s weights: %zu of %zu 16-byte chunks differ (first bad tile %zd) ptr %p\n", when, l, name, bad, tiles * box_rows * 8, (ssize_t)first, (const void*)packed);
+        };
+        tma_view(sl.mapW, sl.w, (size_t)GC * 2 * 64, H / 2, 64, "scan4");
+        if (sl.w3) tma_view(sl.mapW3, sl.w3, (size_t)GC * 128, H / 2, 128, "scan3");
+        if (sl.w5) tma_view(sl.mapW5, sl.w5, (size_t)GC * 2 * 64, H / 2, 64, "pair");
     }
 
     // small batches (<= 64 sessions): two interleaved groups of <= 32 sessions through the latency-optimised pair kernel
@@ -743,16 +768,22 @@ public:
         CK(cudaStreamSynchronize(st));
         CK(cudaMemcpy(h.data(), Mh, n * sizeof(__half), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(h.data() + n, Mh + mall_rows * d.H, n * sizeof(__half), cudaMemcpyDeviceToHost));     // lo plane
-        if (FILE* f = fopen(path, "wb")) { int hdr[4] = { tc + 1, B, d.H, 2 }; fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(__half), h.size(), f); fclose(f); }
+        std::vector<float> g((size_t)tc * B * 4 * d.H);
+        CK(cudaMemcpy(g.data(), b_g.p, g.size() * sizeof(float), cudaMemcpyDeviceToHost));                   // the layer's gate pre-activations
+        if (FILE* f = fopen(path, "wb")) { int hdr[4] = { tc + 1, B, d.H, 2 }; fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(__half), h.size(), f); fwrite(g.data(), sizeof(float), g.size(), f); fclose(f); }
     }
 
     // one layer, steps [t0, t0+tc) of all B sessions of the pass: up to 512 sessions (4 groups of <= 128) per launch
     void scan4_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int H = d.H;
-        const Scan4Layer& sl = s4layers[(size_t)l];
+        static const int dbg_wl = getenv("APRIL_B200_DBG_WL") ? atoi(getenv("APRIL_B200_DBG_WL")) : -1;
+        static const bool dbg_w0 = dbg_wl >= 0, dbg_poison = getenv("APRIL_B200_DBG_POISON") != nullptr, dbg_sync = getenv("APRIL_B200_DBG_SYNC") != nullptr;
+        const Scan4Layer& sl = s4layers[dbg_w0 ? (size_t)dbg_wl : (size_t)l];
         const size_t plane = ((size_t)mall_rows) * H;                      // elements per m plane (sized by run_pass)
         __half *Mh = b_mall.as<__half>(), *Ml = Mh + plane;
         const size_t n0 = (size_t)B * H;
+        if (dbg_poison) { CK(cudaMemsetAsync(Mh + n0, 0x7E, sizeof(__half) * (size_t)tc * n0, st)); CK(cudaMemsetAsync(Ml + n0, 0x7E, sizeof(__half) * (size_t)tc * n0, st)); }
+        if (dbg_sync) CK(cudaDeviceSynchronize());
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
         static const bool no_small = getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "nosmall");   // dev: scan4 for every size
         static int verify_left = getenv("APRIL_B200_VERIFY_W") ? 4 : 0;

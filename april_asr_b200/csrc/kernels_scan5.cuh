@@ -346,5 +346,22 @@ __global__ void pack_weff5_kernel(const float* __restrict__ weff, __half* __rest
     }
 }
 
+// dev aid: what does TMA deliver through a 2-D SWIZZLE_128B map? One CTA per {64 x box_rows} tile: the raw (swizzled) shared-memory image goes to `out`
+__global__ void tma_dump_kernel(const __grid_constant__ CUtensorMap map, uint8_t* out, int box_rows, int nkb) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint8_t* src = smem_raw + (base - smem_u32(smem_raw));
+    __shared__ __align__(8) uint64_t bar_mem;
+    const uint32_t bar = smem_u32(&bar_mem);
+    const int kb = blockIdx.x % nkb, rb = blockIdx.x / nkb;
+    const uint32_t bytes = (uint32_t)box_rows * 128u;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) { mbar_expect_tx(bar, bytes); tma_load_2d(base, &map, bar, kb * 64, rb * box_rows); }
+    mbar_wait(bar, 0);
+    for (uint32_t i = threadIdx.x * 16u; i < bytes; i += blockDim.x * 16u)
+        *reinterpret_cast<uint4*>(out + (size_t)blockIdx.x * bytes + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+
 }  // namespace scan5
 }  // namespace april
