@@ -627,70 +627,6 @@ public:
         CK(cudaFree(dC));
         if (!scan_counters) { CK(cudaMalloc(&scan_counters, 256 * sizeof(unsigned))); owned.push_back(scan_counters); }
         scan4 = true;
-        if (getenv("APRIL_B200_VERIFY_W")) for (int l = 0; l < (int)s4layers.size() && l < 4; l++) verify_packed_weights(l, "after load");
-    }
-
-    // dev aid (APRIL_B200_VERIFY_W): the three packed copies of a layer's W_eff must hold the same numbers
-    void verify_packed_weights(int l, const char* when) {
-        const int H = d.H, GC = H / 8;
-        const Scan4Layer& sl = s4layers[(size_t)l];
-        auto fetch = [&](const __half* p, size_t n) { std::vector<__half> h(n); CK(cudaMemcpy(h.data(), p, n * sizeof(__half), cudaMemcpyDeviceToHost)); return h; };
-        std::vector<float> ref((size_t)4 * H * H, 0.f);
-        {   // scan4 layout (CS = 2): dst[((c * 2 + hl) * NC + n) * Kc + k], n = p * 32 + hc * 16 + gate * 4 + u4, unit = (c / 2) * 16 + p * 8 + hc * 4 + u4, K slice c % 2
-            const int NC = 64, Kc = H / 2;
-            auto w = fetch(sl.w, (size_t)GC * 2 * NC * Kc);
-            for (int c = 0; c < GC; c++) for (int n = 0; n < NC; n++) {
-                const int p = n >> 5, hc = (n >> 4) & 1, g4 = (n >> 2) & 3, u4 = n & 3, unit = (c / 2) * 16 + p * 8 + hc * 4 + u4, r = c % 2;
-                for (int k = 0; k < Kc; k++) ref[((size_t)g4 * H + unit) * H + (size_t)r * Kc + k] = __half2float(w[(((size_t)c * 2 + 0) * NC + n) * Kc + k]) + __half2float(w[(((size_t)c * 2 + 1) * NC + n) * Kc + k]);
-            }
-        }
-        double d3 = 0, d5 = 0;
-        if (sl.w3) {
-            const int KH = H / 2;
-            auto w = fetch(sl.w3, (size_t)GC * 128 * KH);
-            for (int c = 0; c < GC; c++) for (int rho = 0; rho < 64; rho++) {      // hi rows rho, lo rows rho + 64
-                const int half = (rho >> 5) & 1, g4 = (rho >> 3) & 3, u = rho & 7, r = c & 1, pair = c >> 1;
-                for (int k = 0; k < KH; k++) {
-                    const float v = __half2float(w[((size_t)c * 128 + rho) * KH + k]) + __half2float(w[((size_t)c * 128 + 64 + rho) * KH + k]);
-                    d3 = std::max(d3, (double)std::fabs(v - ref[((size_t)g4 * H + pair * 16 + half * 8 + u) * H + (size_t)r * KH + k]));
-                }
-            }
-        }
-        if (sl.w5) {
-            const int Kc = H / 2;
-            auto w = fetch(sl.w5, (size_t)GC * 2 * 64 * Kc);
-            for (int c = 0; c < GC; c++) for (int j = 0; j < 64; j++) {
-                const int cl = c >> 2, p = (c >> 1) & 1, q = c & 1, n = 64 * q + j, o = n >> 5, hc = (n >> 4) & 1, g4 = (n >> 2) & 3, u4 = n & 3, unit = cl * 32 + o * 8 + hc * 4 + u4;
-                for (int k = 0; k < Kc; k++) {
-                    const float v = __half2float(w[(((size_t)c * 2 + 0) * 64 + j) * Kc + k]) + __half2float(w[(((size_t)c * 2 + 1) * 64 + j) * Kc + k]);
-                    d5 = std::max(d5, (double)std::fabs(v - ref[((size_t)g4 * H + unit) * H + (size_t)p * Kc + k]));
-                }
-            }
-        }
-        fprintf(stderr, "verify W (%s) layer %d: max |scan3 - scan4| = %.3g, max |pair - scan4| = %.3g\n", when, l, d3, d5);
-        // ... and TMA must deliver exactly those bytes through the layer's maps
-        auto tma_view = [&](const CUtensorMap& map, const __half* packed, size_t rows, int cols, int box_rows, const char* name) {
-            const int nkb = cols / 64; const size_t tiles = rows / box_rows * nkb, tile_bytes = (size_t)box_rows * 128;
-            uint8_t* dout = nullptr; CK(cudaMalloc(&dout, tiles * tile_bytes));
-            CK(cudaFuncSetAttribute(scan5::tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_bytes + 1024)));
-            scan5::tma_dump_kernel<<<(unsigned)tiles, 128, tile_bytes + 1024, st>>>(map, dout, box_rows, nkb);
-            CK(cudaGetLastError()); CK(cudaStreamSynchronize(st));
-            std::vector<uint8_t> img(tiles * tile_bytes); CK(cudaMemcpy(img.data(), dout, img.size(), cudaMemcpyDeviceToHost)); CK(cudaFree(dout));
-            auto h = fetch(packed, rows * cols);
-            size_t bad = 0, first = (size_t)-1;
-            for (size_t tile = 0; tile < tiles; tile++) {
-                const int kb = (int)(tile % nkb); const size_t rb = tile / nkb;
-                for (int r = 0; r < box_rows; r++) for (int c = 0; c < 8; c++) {
-                    const uint8_t* got = img.data() + tile * tile_bytes + (size_t)r * 128 + (size_t)((c ^ (r & 7)) * 16);
-                    const __half* want = h.data() + (rb * box_rows + r) * cols + kb * 64 + c * 8;
-                    if (memcmp(got, want, 16)) { bad++; if (first == (size_t)-1) first = tile; }
-                }
-            }
-            fprintf(stderr, "verify W (%s) layer %d: TMA view of the %s weights: %zu of %zu 16-byte chunks differ (first bad tile %zd) ptr %p\n", when, l, name, bad, tiles * box_rows * 8, (ssize_t)first, (const void*)packed);
-        };
-        tma_view(sl.mapW, sl.w, (size_t)GC * 2 * 64, H / 2, 64, "scan4");
-        if (sl.w3) tma_view(sl.mapW3, sl.w3, (size_t)GC * 128, H / 2, 128, "scan3");
-        if (sl.w5) tma_view(sl.mapW5, sl.w5, (size_t)GC * 2 * 64, H / 2, 64, "pair");
     }
 
     // small batches (<= 64 sessions): two interleaved groups of <= 32 sessions through the latency-optimised pair kernel
@@ -756,40 +692,17 @@ public:
         }
     }
 
-    // dev aid: APRIL_B200_DUMP_M=<file> writes the hi plane of layer 0's m rows of the first chunk of every pass ([(tc + 1) * B][H] fp16, raw)
-    bool dumped_once = false;
-    static int dump_layer() { static const int l = getenv("APRIL_B200_DUMP_LAYER") ? atoi(getenv("APRIL_B200_DUMP_LAYER")) : 0; return l; }
-    void dump_m_planes(const __half* Mh, int tc, int B) {
-        static const char* path = getenv("APRIL_B200_DUMP_M");
-        if (!path || dumped_once) return;
-        dumped_once = true;
-        const size_t n = (size_t)(tc + 1) * B * d.H;
-        std::vector<__half> h(2 * n);
-        CK(cudaStreamSynchronize(st));
-        CK(cudaMemcpy(h.data(), Mh, n * sizeof(__half), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(h.data() + n, Mh + mall_rows * d.H, n * sizeof(__half), cudaMemcpyDeviceToHost));     // lo plane
-        std::vector<float> g((size_t)tc * B * 4 * d.H);
-        CK(cudaMemcpy(g.data(), b_g.p, g.size() * sizeof(float), cudaMemcpyDeviceToHost));                   // the layer's gate pre-activations
-        if (FILE* f = fopen(path, "wb")) { int hdr[4] = { tc + 1, B, d.H, 2 }; fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(__half), h.size(), f); fwrite(g.data(), sizeof(float), g.size(), f); fclose(f); }
-    }
-
     // one layer, steps [t0, t0+tc) of all B sessions of the pass: up to 512 sessions (4 groups of <= 128) per launch
     void scan4_layer(int l, const float* G, float* mw, float* cw, const int* d_nsteps, int t0, int tc, int B) {
         const int H = d.H;
-        static const int dbg_wl = getenv("APRIL_B200_DBG_WL") ? atoi(getenv("APRIL_B200_DBG_WL")) : -1;
-        static const bool dbg_w0 = dbg_wl >= 0, dbg_poison = getenv("APRIL_B200_DBG_POISON") != nullptr, dbg_sync = getenv("APRIL_B200_DBG_SYNC") != nullptr;
-        const Scan4Layer& sl = s4layers[dbg_w0 ? (size_t)dbg_wl : (size_t)l];
+        const Scan4Layer& sl = s4layers[(size_t)l];
         const size_t plane = ((size_t)mall_rows) * H;                      // elements per m plane (sized by run_pass)
         __half *Mh = b_mall.as<__half>(), *Ml = Mh + plane;
         const size_t n0 = (size_t)B * H;
-        if (dbg_poison) { CK(cudaMemsetAsync(Mh + n0, 0x7E, sizeof(__half) * (size_t)tc * n0, st)); CK(cudaMemsetAsync(Ml + n0, 0x7E, sizeof(__half) * (size_t)tc * n0, st)); }
-        if (dbg_sync) CK(cudaDeviceSynchronize());
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
         static const bool no_small = getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "nosmall");   // dev: scan4 for every size
-        static int verify_left = getenv("APRIL_B200_VERIFY_W") ? 4 : 0;
-        if (verify_left > 0 && l < 4) { verify_left--; CK(cudaStreamSynchronize(st)); verify_packed_weights(l, "at first use"); }
-        if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B); return; }
-        if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B); return; }
+        if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); return; }
+        if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
         const int per_launch = scan4::MAXG * scan4::GROUP;
         for (int g0 = 0; g0 < B; g0 += per_launch) {
@@ -815,7 +728,6 @@ public:
             launch_check();
             if (do_trace) dump_trace(a.GC, tc, 1);
         }
-        if (l == dump_layer() && t0 == 0) dump_m_planes(Mh, tc, B);
     }
 
     // the radix-8 front-end serves the 512-sample window (every model of the reference: 25 ms at 16 kHz); other windows take the generic kernel
