@@ -196,7 +196,8 @@ public:
     int scan4_cs = 2, scan4_mmaw = 2;
     size_t scan4_smem = 0;
     bool scan3 = false;             // small-batch kernel (kernels_scan3.cuh) available: used for passes of <= 64 sessions
-    bool scan5 = false;             // pair kernel (kernels_scan5.cuh) available: used for passes of > 128 sessions
+    bool scan5 = false;             // pair kernel (kernels_scan5.cuh) available: used for passes of >= scan5_min sessions
+    int scan5_min = 257;
     size_t scan5_smem = 0;
     size_t scan3_smem = 0;
     size_t mall_rows = 0;           // rows per m plane of the current pass chunking: (Tc + 1) * B
@@ -574,7 +575,9 @@ public:
             cudaGetLastError();
         }
         {   // the pair kernel: clusters of 4, all co-resident
-            static const bool off = !(getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "pair"));   // opt-in until validated on hardware
+            const char* sel = getenv("APRIL_B200_SCAN");
+            const bool off = sel && !strcmp(sel, "nopair");                 // dev: scan4 for every large batch
+            scan5_min = (sel && !strcmp(sel, "pair")) ? 129 : 257;          // measured on B200 (profiles/r02e, r02g): a tie at 256 sessions, 18 % faster at 512; "pair" forces it from 129
             scan5_smem = scan5::smem_bytes(H);
             scan5 = !off && H % 128 == 0 && GC % scan5::CL == 0 && scan5_smem <= 227 * 1024 &&
                     cudaFuncSetAttribute(scan5::lstm_scan5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan5_smem) == cudaSuccess;
@@ -702,7 +705,7 @@ public:
         scan4::scan4_prepare_kernel<<<(unsigned)std::min<size_t>((n0 / 4 + 255) / 256, (size_t)num_sms * 4), 256, 0, st>>>(mw, Mh, Ml, n0); launch_check();
         static const bool no_small = getenv("APRIL_B200_SCAN") && !strcmp(getenv("APRIL_B200_SCAN"), "nosmall");   // dev: scan4 for every size
         if (scan3 && B <= 64 && !no_small) { scan3_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, plane, l); return; }
-        if (scan5 && B > 128) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); return; }
+        if (scan5 && B >= scan5_min) { scan5_layer(sl, G, mw, cw, d_nsteps, t0, tc, B, Mh, Ml, l); return; }
         static const int groups_env = getenv("APRIL_B200_SCAN_GROUPS") ? atoi(getenv("APRIL_B200_SCAN_GROUPS")) : 0;
         const int per_launch = scan4::MAXG * scan4::GROUP;
         for (int g0 = 0; g0 < B; g0 += per_launch) {

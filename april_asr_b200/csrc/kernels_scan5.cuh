@@ -39,8 +39,8 @@ constexpr int NB = 64;              // ... of which one CTA holds 64 (owners 2 q
 constexpr int HALF = 128;           // sessions per CTA of a pair = its half of M = 256
 constexpr int ITEM = 256;           // sessions per item
 constexpr int MAXI = 2;             // items per launch (512 sessions)
-constexpr int EPI_WARPS = 16;       // four per TMEM lane quarter: each thread finishes 4 units of its session (measured: with 8 warps x 8 units the
-                                    // epilogue paced the kernel at 9.4 us per 256-session item)
+constexpr int EPI_WARPS = 8;        // two per TMEM lane quarter: each thread finishes 8 units of its session (measured: 16 warps x 4 units are
+                                    // slower at every batch size, 20.4 vs 18.2 us per layer-step at 512 sessions: profiles/r02g_pair_epilogue_sweep.log)
 constexpr int MMAW = 2;             // issuing warps (leader only) = accumulators per item
 constexpr int RST = 4;              // ring stages of one 16 KB tile
 constexpr int NSLOT = 512 / (MMAW * NCT);   // 2 accumulator sets
@@ -178,15 +178,14 @@ lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                 }
         }
     } else if (warp < 1 + MMAW + EPI_WARPS) {
-        // ===================== epilogue: one thread = one of my 128 sessions x 4 units (16 columns [gate][u4] of one owner block) =====================
-        // four warps per TMEM lane quarter: (hf, hc) = which of my two owner blocks, which half of its 8 units
+        // ===================== epilogue: one thread = one of my 128 sessions x 8 units (one owner block of 32 columns) =====================
         const int ew = warp - (1 + MMAW);
-        const int qt = warp & 3, hq = ew >> 2, hf = hq >> 1, hc = hq & 1;
+        const int qt = warp & 3, hf = ew >> 2;                             // TMEM lane quarter; which of my two owner blocks
         const int sl = qt * 32 + lane;                                     // session lane within my half
         const uint32_t lane_off = (uint32_t)(qt * 32) << 16;
         const uint32_t own_mine = 2u * p + (uint32_t)hf, own_send = 2u * (1u - p) + (uint32_t)hf;   // owner blocks: columns [32 o, 32 o + 32)
-        const int ucol = ((int)blockIdx.x / CL) * 32 + (int)own_mine * 8 + hc * 4;   // first of my 4 units
-        float cst[MAXI][4];
+        const int ucol = ((int)blockIdx.x / CL) * 32 + (int)own_mine * 8;  // first of my 8 units
+        float cst[MAXI][8];
         int nlive[MAXI];
 #pragma unroll
         for (int g = 0; g < MAXI; g++) {
@@ -194,11 +193,13 @@ lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
             const bool valid = g < NG && si < a.Bg[g];
             const int sess = a.g0 + a.goff[g] + si;
             nlive[g] = valid ? a.nsteps[sess] : 0;
-            const float4 c4 = valid ? *reinterpret_cast<const float4*>(a.c_state + (size_t)sess * a.H + ucol) : make_float4(0.f, 0.f, 0.f, 0.f);
-            cst[g][0] = c4.x; cst[g][1] = c4.y; cst[g][2] = c4.z; cst[g][3] = c4.w;
+#pragma unroll
+            for (int h4 = 0; h4 < 2; h4++) {
+                const float4 c4 = valid ? *reinterpret_cast<const float4*>(a.c_state + (size_t)sess * a.H + ucol + 4 * h4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cst[g][4 * h4] = c4.x; cst[g][4 * h4 + 1] = c4.y; cst[g][4 * h4 + 2] = c4.z; cst[g][4 * h4 + 3] = c4.w;
+            }
         }
         const uint32_t tempty_leader0 = mapa_(tempty_bar(0), leader), prfull_peer = mapa_(prfull_bar, kpeer), prfree_peer = mapa_(prfree_bar, kpeer);
-        const uint32_t xoff = (uint32_t)((hf * 8 + hc * 4) * HALF + sl) * 16u;   // my four 16-byte chunks of the exchange block: + c * HALF * 16
         for (int t = 0; t < a.T; t++) {
 #pragma unroll
             for (int g = 0; g < MAXI; g++) {
@@ -213,31 +214,33 @@ lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                 if (ew == 0 && lane == 0) TRACE5(4);
                 tc_fence_after();
                 if (item > 0) mbar_wait_cluster(prfree_bar, (item - 1) & 1);                 // the K partner is done with what it received last item
-                float mine[16];
+                float mine[32];
 #pragma unroll
-                for (int j = 0; j < 16; j++) mine[j] = 0.f;
+                for (int j = 0; j < 32; j++) mine[j] = 0.f;
                 if (warp_valid) {
-                    const uint32_t tb = tmem_base + lane_off + (uint32_t)(slot * MMAW * NCT) + (uint32_t)hc * 16u;
-                    {                                                      // the partner's columns first: they have the longer way
+                    const uint32_t tb = tmem_base + lane_off + (uint32_t)(slot * MMAW * NCT);
+#pragma unroll
+                    for (int h16 = 0; h16 < 2; h16++) {                    // the partner's columns first: they have the longer way
                         uint32_t r0[16], r1[16];
-                        tmem_ld16_nowait(tb + own_send * 32u, r0);
-                        tmem_ld16_nowait(tb + (uint32_t)NCT + own_send * 32u, r1);
+                        tmem_ld16_nowait(tb + own_send * 32u + (uint32_t)h16 * 16u, r0);
+                        tmem_ld16_nowait(tb + (uint32_t)NCT + own_send * 32u + (uint32_t)h16 * 16u, r1);
                         tc_wait_ld();
                         if (valid) {
-                            const uint32_t dst = mapa_(exr0 + xoff, kpeer);
+                            const uint32_t dst = mapa_(exr0 + (uint32_t)((hf * 8 + h16 * 4) * HALF + sl) * 16u, kpeer);
 #pragma unroll
                             for (int c = 0; c < 4; c++)
                                 st_remote_v4(dst + (uint32_t)c * (HALF * 16u), __uint_as_float(r0[4 * c]) + __uint_as_float(r1[4 * c]), __uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]),
                                              __uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]), __uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]));
                         }
                     }
-                    {
+#pragma unroll
+                    for (int h16 = 0; h16 < 2; h16++) {
                         uint32_t r0[16], r1[16];
-                        tmem_ld16_nowait(tb + own_mine * 32u, r0);
-                        tmem_ld16_nowait(tb + (uint32_t)NCT + own_mine * 32u, r1);
+                        tmem_ld16_nowait(tb + own_mine * 32u + (uint32_t)h16 * 16u, r0);
+                        tmem_ld16_nowait(tb + (uint32_t)NCT + own_mine * 32u + (uint32_t)h16 * 16u, r1);
                         tc_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; j++) mine[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                        for (int j = 0; j < 16; j++) mine[16 * h16 + j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
                     }
                 }
                 tc_fence_before();
@@ -247,18 +250,20 @@ lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                     mbar_arrive_remote(prfull_peer);
                 }
                 if (ew == 0 && lane == 0) TRACE5(5);
-                // input gates of my 4 units: in flight while the partner's partial sums arrive
-                float4 gin[4];
+                // input gates of my 8 units: in flight while the partner's partial sums arrive. Column block layout: [hc][gate][u4]
+                float4 gin[2][4];
                 if (valid) {
                     const float* gp = a.G + ((size_t)t * a.Bs + sess) * 4 * a.H + ucol;
 #pragma unroll
-                    for (int g4 = 0; g4 < 4; g4++) gin[g4] = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)g4 * a.H));
+                    for (int hc = 0; hc < 2; hc++)
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; g4++) gin[hc][g4] = __ldcs(reinterpret_cast<const float4*>(gp + (size_t)g4 * a.H + 4 * hc));
                 }
                 mbar_wait_cluster(prfull_bar, item & 1);                   // the other K half's sums for my units
                 if (valid) {
-                    const float4* xr = reinterpret_cast<const float4*>(gptr(exr0 + xoff));
+                    const float4* xr = reinterpret_cast<const float4*>(gptr(exr0 + (uint32_t)((hf * 8) * HALF + sl) * 16u));
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
+                    for (int c = 0; c < 8; c++) {
                         const float4 x = xr[(size_t)c * HALF];
                         mine[4 * c] += x.x; mine[4 * c + 1] += x.y; mine[4 * c + 2] += x.z; mine[4 * c + 3] += x.w;
                     }
@@ -268,24 +273,30 @@ lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
                 if (ew == 0 && lane == 0) TRACE5(6);
                 if (valid) {
                     const bool live = a.t0 + t < nlive[g];
-                    __align__(8) __half mh[4], ml[4];
-                    float mval[4];
-                    const float xi[4] = { gin[0].x, gin[0].y, gin[0].z, gin[0].w }, xf[4] = { gin[1].x, gin[1].y, gin[1].z, gin[1].w },
-                                xg[4] = { gin[2].x, gin[2].y, gin[2].z, gin[2].w }, xo[4] = { gin[3].x, gin[3].y, gin[3].z, gin[3].w };
+                    __align__(16) __half mh[8], ml[8];
+                    float mval[8];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {                          // mine: [gate][u4]
-                        const float pi = mine[u] * a.inv_scale + xi[u], pf = mine[4 + u] * a.inv_scale + xf[u];
-                        const float pg = mine[8 + u] * a.inv_scale + xg[u], po = mine[12 + u] * a.inv_scale + xo[u];
-                        const float cn = fast_sigmoid(pf) * cst[g][u] + fast_sigmoid(pi) * fast_tanh(pg);
-                        mval[u] = fast_sigmoid(po) * fast_tanh(cn);
-                        if (live) cst[g][u] = cn;
-                        split_f16(mval[u], mh[u], ml[u]);
+                    for (int hc = 0; hc < 2; hc++) {
+                        const float xi[4] = { gin[hc][0].x, gin[hc][0].y, gin[hc][0].z, gin[hc][0].w }, xf[4] = { gin[hc][1].x, gin[hc][1].y, gin[hc][1].z, gin[hc][1].w },
+                                    xg[4] = { gin[hc][2].x, gin[hc][2].y, gin[hc][2].z, gin[hc][2].w }, xo[4] = { gin[hc][3].x, gin[hc][3].y, gin[hc][3].z, gin[hc][3].w };
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float* mm = mine + 16 * hc;              // [gate][u4]
+                            const float pi = mm[u] * a.inv_scale + xi[u], pf = mm[4 + u] * a.inv_scale + xf[u];
+                            const float pg = mm[8 + u] * a.inv_scale + xg[u], po = mm[12 + u] * a.inv_scale + xo[u];
+                            const float cn = fast_sigmoid(pf) * cst[g][4 * hc + u] + fast_sigmoid(pi) * fast_tanh(pg);
+                            mval[4 * hc + u] = fast_sigmoid(po) * fast_tanh(cn);
+                            if (live) cst[g][4 * hc + u] = cn;
+                            split_f16(mval[4 * hc + u], mh[4 * hc + u], ml[4 * hc + u]);
+                        }
                     }
                     const size_t orow = ((size_t)(t + 1) * a.Bs + sess) * a.H + ucol;
-                    *reinterpret_cast<uint2*>(a.Mx_hi + orow) = *reinterpret_cast<const uint2*>(mh);
-                    *reinterpret_cast<uint2*>(a.Mx_lo + orow) = *reinterpret_cast<const uint2*>(ml);
-                    if (live && ((a.t0 + t == nlive[g] - 1) || (t == a.T - 1)))
+                    *reinterpret_cast<uint4*>(a.Mx_hi + orow) = *reinterpret_cast<const uint4*>(mh);
+                    *reinterpret_cast<uint4*>(a.Mx_lo + orow) = *reinterpret_cast<const uint4*>(ml);
+                    if (live && ((a.t0 + t == nlive[g] - 1) || (t == a.T - 1))) {
                         *reinterpret_cast<float4*>(a.m_state + (size_t)sess * a.H + ucol) = make_float4(mval[0], mval[1], mval[2], mval[3]);
+                        *reinterpret_cast<float4*>(a.m_state + (size_t)sess * a.H + ucol + 4) = make_float4(mval[4], mval[5], mval[6], mval[7]);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(rel_bar(g));
@@ -294,8 +305,11 @@ lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 *
 #pragma unroll
         for (int g = 0; g < MAXI; g++) {
             const int si = (int)q * HALF + sl;
-            if (g < NG && si < a.Bg[g])
-                *reinterpret_cast<float4*>(a.c_state + (size_t)(a.g0 + a.goff[g] + si) * a.H + ucol) = make_float4(cst[g][0], cst[g][1], cst[g][2], cst[g][3]);
+            if (g < NG && si < a.Bg[g]) {
+                float* cp = a.c_state + (size_t)(a.g0 + a.goff[g] + si) * a.H + ucol;
+                *reinterpret_cast<float4*>(cp) = make_float4(cst[g][0], cst[g][1], cst[g][2], cst[g][3]);
+                *reinterpret_cast<float4*>(cp + 4) = make_float4(cst[g][4], cst[g][5], cst[g][6], cst[g][7]);
+            }
         }
     } else {
         // ===================== releaser: the gpu-scope release (store acknowledgement ~1 us) must not hold the epilogue =====================

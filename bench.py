@@ -306,8 +306,12 @@ def main():
         gemm_tf = st.gemm_flops / max(1e-9, st.gemm_ms / 1e3) / 1e12
         whole_tf = sess_steps * FLOP_PER_STEP_ENCODER / max(1e-9, st.compute_ms / 1e3) / 1e12
         layer_steps = max(1.0, (sess_steps / r["S"]) * 12)
-        tr = ncu_traffic("lstm_scan4_kernel")
-        return {"bound": "tensor", "kernel": "scan4::lstm_scan4_kernel (recurrent W_hh / W_hr part of one LSTM layer: all steps of a pass, up to 512 sessions per launch; %.0f %% of the step)" % (100.0 * st.lstm_scan_ms / max(1e-9, st.compute_ms)),
+        # the engine picks the scan kernel by the pass's session count (engine.cu: scan4_layer)
+        if r["S"] <= 64: kname, kdesc = "lstm_scan3_kernel", "scan3::lstm_scan3_kernel (<= 64 sessions: latency-optimised CTA pairs, W_eff stacked on the UMMA M dimension)"
+        elif r["S"] <= 256: kname, kdesc = "lstm_scan4_kernel", "scan4::lstm_scan4_kernel (65-256 sessions: sessions on the UMMA M dimension, K split across a 2-CTA cluster)"
+        else: kname, kdesc = "lstm_scan5_kernel", "scan5::lstm_scan5_kernel (> 256 sessions: cta_group::2 pair MMAs, items of 256 sessions, cluster of 4)"
+        tr = ncu_traffic(kname)
+        return {"bound": "tensor", "kernel": kdesc + "; the recurrent W_hh / W_hr part of one LSTM layer, all steps of a pass per launch; %.0f %% of the step" % (100.0 * st.lstm_scan_ms / max(1e-9, st.compute_ms)),
                 "achieved": scan_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": scan_tf / peak_tf,
                 "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "traffic": tr["bytes"] if tr else None,

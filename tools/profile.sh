@@ -11,7 +11,7 @@ cap() {   # name, kernel regex (demangled name), launch-skip, extra bench args
   ncu -i $OUT/$1.ncu-rep --page raw --csv > $OUT/$1.raw.csv 2>/dev/null
 }
 cap scan3_b64 lstm_scan3_kernel 0 ""
-cap scan4_b512 lstm_scan4_kernel 0 "--sessions 512"
+cap scan4_b200 lstm_scan4_kernel 0 "--sessions 200"
 cap scan5_b512 lstm_scan5_kernel 0 "--sessions 512"
 cap gemm_wih "gemm_tc_kernel<.int.3, .int.0, .int.2>" 1 ""
 cap greedy greedy_cluster_kernel 0 ""
