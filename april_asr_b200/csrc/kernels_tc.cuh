@@ -380,6 +380,13 @@ __global__ void split_rows_kernel(const float* __restrict__ x, __half* __restric
     }
 }
 
+// weights at load time: x * sc (a power of two: exact) as an fp16 (hi, lo) pair; the same roundings as the host would do
+__global__ void split_scale_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n, float sc) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) split_f16(x[i] * sc, hi[i], lo[i]);
+}
+
 // y = a + b, plus split copies
 __global__ void add_rows_split_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
                                       __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {

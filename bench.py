@@ -245,7 +245,9 @@ def main():
 
     path = ensure_model(rank, dist)
     lib = A.Lib()
+    t_load = time.perf_counter()
     m = A.Model(path, lib)
+    t_load = time.perf_counter() - t_load      # aam_create_model: parse, upload, fp16 splits, W_eff fold, decoder table
     handler = ctypes.cast(lib.c.aab_counting_handler, A.HANDLER)
     pk, pk_src = peaks()
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
@@ -411,7 +413,7 @@ def main():
             "e2e": {"value": frames_total / wall_s, "unit": "frames/s", "ms_per_step": 1000.0 * wall_s / a.steps,
                     "h2d_bytes_per_step": st.h2d_bytes / a.steps, "d2h_bytes_per_step": st.d2h_bytes / a.steps,
                     "x_realtime_per_stream": a.seconds / (wall_s / a.steps)},
-            "gpu_launches": int(st.kernel_launches),
+            "gpu_launches": int(st.kernel_launches), "model_load_s": t_load,
             "clocks": r["clocks"],
             "comm": {"backend": "nccl" if world > 1 else None, "nranks": world, "use": "start/stop barrier and max-over-ranks of the timings only"},
             "roofline": roofline_of(r, a.steps),

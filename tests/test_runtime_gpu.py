@@ -229,3 +229,40 @@ def test_sessions_are_placed_on_every_gpu_of_the_box():
     m.close()
     for i, (c, w) in enumerate(zip(cols, want)):
         assert c.keys() == w.keys(), "session %d (cuda:%d) differs from the oracle" % (i, devs[i])
+
+
+def test_damaged_model_files_never_crash_the_full_load_path(tmp_path):
+    """The CPU suite feeds truncated and bit-damaged `.april` files to the parser alone; here the same damage goes through
+    `aam_create_model` (src/april_model.c:24-107's role: parse, upload, fp16 splits, W_eff fold, decoder table). Truncations must
+    give NULL; random damage may load (weights are just numbers) or not, but the call must return and a loaded model must be
+    freeable. Run in a subprocess so that a crash is a failing return code."""
+    import os, subprocess, sys
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import common as C
+lib = C.product_lib()
+good = open(C.TINY_MODEL, "rb").read()
+out = sys.argv[1]
+def load(data):
+    p = os.path.join(out, "m.april"); open(p, "wb").write(data)
+    h = lib.c.aam_create_model(p.encode())
+    if h: lib.c.aam_free(h)
+    return bool(h)
+assert load(good)
+n_bad = sum(not load(good[:cut]) for cut in [0, 7, 12, 64, 1000, len(good) // 3, len(good) // 2, len(good) - 1000, len(good) - 1])
+rs = np.random.RandomState(11)
+loaded = 0
+for trial in range(60):
+    b = bytearray(good)
+    region = [(0, 64), (0, 4096), (0, len(good)), (len(good) - 20000, len(good)), (len(good) // 2 - 4096, len(good) // 2 + 4096)][trial %% 5]
+    for _ in range(1 + trial %% 7):
+        b[rs.randint(region[0], region[1])] = rs.randint(0, 256)
+    loaded += load(bytes(b))
+print("truncations rejected:", n_bad, "damaged files that still loaded:", loaded)
+assert n_bad >= 8
+assert load(good)                       # and the library is still usable afterwards
+''' % (C.ROOT, os.path.join(C.ROOT, "tests"), os.path.join(C.ROOT, "tools"))
+    r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-300:], r.stderr[-1200:])
