@@ -17,6 +17,7 @@
 #include "kernels_scan4.cuh"
 #include "kernels_scan3.cuh"
 #include "kernels_scan5.cuh"
+#include "kernels_greedy_pair.cuh"
 
 namespace april {
 
@@ -196,6 +197,10 @@ public:
     int scan4_cs = 2, scan4_mmaw = 2;
     size_t scan4_smem = 0;
     bool scan3 = false;             // small-batch kernel (kernels_scan3.cuh) available: used for passes of <= 64 sessions
+    bool pair_greedy = false;       // kernels_greedy_pair.cuh available
+    int pair_greedy_min = 1 << 30;  // passes of at least this many sessions use it (set after measurement; APRIL_B200_GREEDY=pair|cluster forces)
+    int gp_Rh = 0;
+    size_t gp_smem = 0;
     bool scan5 = false;             // pair kernel (kernels_scan5.cuh) available: used for passes of >= scan5_min sessions
     int scan5_min = 257;
     size_t scan5_smem = 0;
@@ -414,6 +419,12 @@ public:
         CK(cudaFree(Y));
         CK(cudaFuncSetAttribute(k::greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gr_smem));
         fast_greedy = true;
+        // the CTA-pair search kernel (joiner rows streamed from L2): needs the same table and J <= 512
+        gp_Rh = (V + 1) / 2;
+        gp_smem = k::greedy_pair_smem(J, V, gp_Rh);
+        pair_greedy = V >= 2 && gp_smem <= 227 * 1024 && cudaFuncSetAttribute(k::greedy_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp_smem) == cudaSuccess;
+        cudaGetLastError();
+        if (const char* g = getenv("APRIL_B200_GREEDY")) { if (!strcmp(g, "cluster")) pair_greedy_min = 1 << 30; else if (!strcmp(g, "pair")) pair_greedy_min = 1; }
     }
 
     size_t conv_smem() const {
@@ -1087,7 +1098,13 @@ public:
                 else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
                 span_begin(2);
-                if (fast_greedy) {
+                if (fast_greedy && pair_greedy && B >= pair_greedy_min) {
+                    const int maxp = std::max(1, num_sms / 2);
+                    const int S = std::min(k::GP_MAX_S, std::max(1, (B + maxp - 1) / maxp));     // one wave of CTA pairs
+                    const int npair = (B + S - 1) / S;
+                    k::greedy_pair_kernel<<<npair * 2, k::GP_THREADS, gp_smem, st>>>(jp, dtab, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate,
+                                                                                      b_rec.as<k::DecisionRecord>(), b_np.as<int>(), want_tap ? b_tap.as<float>() : nullptr, last, tc, S, gp_Rh);
+                } else if (fast_greedy) {
                     const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
                     const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));
                     const int ncl = (B + S - 1) / S;

@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--soak-minutes", type=float, default=60.0, help="audio minutes per session in --mode soak")
     ap.add_argument("--soak-chunk", type=float, default=10.0, help="audio seconds per feed call in --mode soak")
     ap.add_argument("--ticks", type=int, default=250)
+    ap.add_argument("--lanes", type=int, default=0, help="ONE process driving this many GPUs through the library's own placement (SURVEY.md par. 8e): sessions x lanes streams, no torchrun; 0 = one process per GPU")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,7 +238,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    os.environ["APRIL_B200_DEVICE"] = str(local)       # one process per GPU: pin this process's models to its device
+    if a.lanes > 0:
+        assert world == 1, "--lanes is the single-process layout"
+        os.environ.pop("APRIL_B200_DEVICE", None); os.environ.pop("LOCAL_RANK", None)
+        os.environ["APRIL_B200_MAX_DEVICES"] = str(a.lanes)      # aam_create_model builds one engine per device; aas_create_session picks the least-loaded
+    else:
+        os.environ["APRIL_B200_DEVICE"] = str(local)   # one process per GPU: pin this process's models to its device
     import april_asr_b200 as A
     import stream_driver as SD
     from april_asr_b200 import _ffi, dist_util
@@ -395,6 +401,19 @@ def main():
             dist.destroy_process_group()
         return
 
+    if a.lanes > 0:
+        # single process, all GPUs: the batched calls span the lanes, whose passes run concurrently; times are the max over lanes (aab_get_stats)
+        S = a.sessions * a.lanes
+        r = run_bulk(S, a.seconds, a.warmup, a.steps, list(range(S)))
+        st = r["st"]
+        frames = S * FRAMES_PER_STREAM(r["n"]) * a.steps
+        print(json.dumps({"metric": "audio_frames_per_sec", "mode": "lanes", "value": frames / (st.compute_ms / 1e3), "unit": "frames/s", "n_gpus": a.lanes, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": st.compute_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16x3-split tensor-core products)", "data": "synthetic",
+                          "config": {"workload": workload, "sessions_per_gpu": a.sessions, "layout": "ONE process, %d GPUs, sessions placed by the library (least-loaded lane), per-lane passes of one batched call run concurrently; no collective" % a.lanes},
+                          "e2e": {"value": frames / sum(r["walls"]), "unit": "frames/s", "ms_per_step": 1e3 * sum(r["walls"]) / a.steps, "h2d_bytes_per_step": st.h2d_bytes / a.steps, "d2h_bytes_per_step": st.d2h_bytes / a.steps},
+                          "gpu_launches": int(st.kernel_launches), "model_load_s": t_load, "clocks": r["clocks"], "final_tokens": r["counters"][3]}))
+        m.close()
+        return
     r = run_bulk(a.sessions, a.seconds, a.warmup, a.steps, dist_util.shard_stream_ids(rank, world, a.sessions))
     st = r["st"]
     (wall_s, compute_s), (frames_step,) = dist_util.combine(dist, "cuda", [sum(r["walls"]), st.compute_ms / 1e3], [a.sessions * FRAMES_PER_STREAM(r["n"])])
