@@ -159,6 +159,10 @@ public:
     Params prm;
     int dev = 0;
     int num_sms = 148;
+    int sm_budget = 148;              // SMs the persistent GEMM grids may count on: num_sms minus those lent to the search kernel running beside the encoder
+    cudaStream_t st2 = nullptr;       // the search of time chunk c runs here, under the encoder of chunk c + 1 (run_pass)
+    bool overlap_search = false;      // APRIL_B200_OVERLAP
+    int overlap_chunks = 4;
     cudaStream_t st = nullptr;
     std::mutex mu;
     EngineStats stat;
@@ -170,8 +174,8 @@ public:
     std::vector<cudaEvent_t> ev_pool;
     std::vector<Span> spans;
     cudaEvent_t ev_get() { if (ev_pool.empty()) { cudaEvent_t e; CK(cudaEventCreate(&e)); return e; } cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
-    void span_begin(int cls) { if (!profile) return; Span sp{ ev_get(), ev_get(), cls }; CK(cudaEventRecord(sp.a, st)); spans.push_back(sp); }
-    void span_end() { if (!profile) return; CK(cudaEventRecord(spans.back().b, st)); }
+    void span_begin(int cls, cudaStream_t on = nullptr) { if (!profile) return; Span sp{ ev_get(), ev_get(), cls }; CK(cudaEventRecord(sp.a, on ? on : st)); spans.push_back(sp); }
+    void span_end(cudaStream_t on = nullptr) { if (!profile) return; CK(cudaEventRecord(spans.back().b, on ? on : st)); }
     void spans_collect() {
         for (auto& sp : spans) { float ms = 0; CK(cudaEventElapsedTime(&ms, sp.a, sp.b)); if (sp.cls == 0) stat.gemm_ms += ms; else if (sp.cls == 1) stat.lstm_scan_ms += ms; else if (sp.cls == 2) stat.greedy_ms += ms; else if (sp.cls == 3) { stat.gemm_ms += ms; stat.lstm_gemm_ms += ms; } else stat.frontend_ms += ms; ev_pool.push_back(sp.a); ev_pool.push_back(sp.b); }
         spans.clear();
@@ -198,7 +202,8 @@ public:
     size_t scan4_smem = 0;
     bool scan3 = false;             // small-batch kernel (kernels_scan3.cuh) available: used for passes of <= 64 sessions
     bool pair_greedy = false;       // kernels_greedy_pair.cuh available
-    int pair_greedy_min = 1 << 30;  // passes of at least this many sessions use it (set after measurement; APRIL_B200_GREEDY=pair|cluster forces)
+    int pair_greedy_min = 257;      // passes of at least this many sessions use it (measured, profiles/r02j: 160 sessions 31.3 vs 26.9 ms for the 8-CTA clusters,
+                                    // 512 sessions 40.6 vs 74.9 ms); APRIL_B200_GREEDY=pair|cluster forces one of them
     int gp_Rh = 0;
     size_t gp_smem = 0;
     bool scan5 = false;             // pair kernel (kernels_scan5.cuh) available: used for passes of >= scan5_min sessions
@@ -265,7 +270,9 @@ public:
         CK(cudaGetDeviceProperties(&prop, dev));
         if (prop.major != 10) { err = "this build targets sm_100a (B200); device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor); return false; }
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        num_sms = prop.multiProcessorCount;
+        num_sms = prop.multiProcessorCount; sm_budget = num_sms;
+        { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, hi)); }   // its few CTAs are placed before the encoder's next kernel fills the GPU
+        if (const char* o = getenv("APRIL_B200_OVERLAP")) { overlap_search = atoi(o) > 0; if (atoi(o) > 1) overlap_chunks = atoi(o); }
         profile = getenv("APRIL_B200_TIMING") != nullptr;
         if (d.D % 16 || d.H % 16 || d.F % 16 || d.J % 16 || (d.C3 * d.F3) % 16) { err = "model dims must be multiples of 16"; return false; }
 
@@ -437,6 +444,7 @@ public:
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
         for (void* p : owned) cudaFree(p);
         cudaFree(dout_blank); cudaFree(dtab); cudaFree(m_store); cudaFree(h_store); cudaFree(c_store); cudaFree(dout_store); cudaFree(carry_store); cudaFree(gstate);
+        if (st2) cudaStreamDestroy(st2);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -557,10 +565,7 @@ public:
         if (cudaFuncSetAttribute(scan4::lstm_scan4_kernel<CS, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan4::Cfg<CS, MW>::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int ncl = 0;
+        int ncl = 0;                                               // cluster dims are compiled in
         if (cudaOccupancyMaxActiveClusters(&ncl, scan4::lstm_scan4_kernel<CS, MW>, &cfg) != cudaSuccess || ncl * CS < GC) { cudaGetLastError(); return false; }   // every cluster must be co-resident
         scan4_smem = smem;
         return true;
@@ -568,10 +573,9 @@ public:
     template <int CS, int MW> void scan4_launch(const Scan4Layer& sl, const CUtensorMap& mh, const CUtensorMap& ml, const scan4::Args& a) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan4::Cfg<CS, MW>::THREADS); cfg.dynamicSmemBytes = scan4_smem; cfg.stream = st;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = capturing ? 1 : 2;          // graph capture: plain launch (co-residency was checked at init: 1 CTA per SM, grid <= SMs)
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = capturing ? 0 : 1;          // graph capture: plain launch (co-residency was checked at init: 1 CTA per SM, grid <= SMs)
         CK(cudaLaunchKernelEx(&cfg, scan4::lstm_scan4_kernel<CS, MW>, sl.mapW, mh, ml, a));
     }
 
@@ -603,9 +607,6 @@ public:
             if (scan5) {
                 cudaLaunchConfig_t cfg{};
                 cfg.gridDim = dim3((unsigned)GC); cfg.blockDim = dim3(scan5::THREADS); cfg.dynamicSmemBytes = scan5_smem; cfg.stream = st;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = scan5::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.attrs = at; cfg.numAttrs = 1;
                 int ncl = 0;
                 if (cudaOccupancyMaxActiveClusters(&ncl, scan5::lstm_scan5_kernel, &cfg) != cudaSuccess || ncl * scan5::CL < GC) scan5 = false;
             }
@@ -704,10 +705,9 @@ public:
             const CUtensorMap mh = make_map_f16(Mh, (uint64_t)(tc + 1) * B, (uint64_t)H, scan5::HALF), ml = make_map_f16(Ml, (uint64_t)(tc + 1) * B, (uint64_t)H, scan5::HALF);
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)a.GC); cfg.blockDim = dim3(scan5::THREADS); cfg.dynamicSmemBytes = scan5_smem; cfg.stream = st;
-            cudaLaunchAttribute at[2];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = scan5::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-            cfg.attrs = at; cfg.numAttrs = capturing ? 1 : 2;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+            cfg.attrs = at; cfg.numAttrs = capturing ? 0 : 1;      // cluster dims are compiled in
             CK(cudaLaunchKernelEx(&cfg, scan5::lstm_scan5_kernel, sl.mapW5, mh, ml, a));
             launch_check();
             if (do_trace) dump_trace(a.GC, tc, 2);
@@ -786,10 +786,10 @@ public:
         tc::GemmArgs g{ M, w.N, w.K, w.inv_scale, bias, residual, out_f32, out_hi, out_lo };
         if (pair) {
             const int work = ((tiles_m + 1) / 2) * tiles_n;
-            const unsigned grid = 2u * (unsigned)std::min(work, num_sms / 2);
+            const unsigned grid = 2u * (unsigned)std::min(work, sm_budget / 2);
             if (npass == 3) gemm_tc_epi<3, 2>(epi, grid, mAh, mAl, mBh, mBl, g); else gemm_tc_epi<1, 2>(epi, grid, mAh, mAl, mBh, mBl, g);
         } else {
-            const unsigned grid = (unsigned)std::min(tiles_m * tiles_n, num_sms);
+            const unsigned grid = (unsigned)std::min(tiles_m * tiles_n, sm_budget);
             if (npass == 3) gemm_tc_epi<3, 1>(epi, grid, mAh, mAl, mBh, mBl, g); else gemm_tc_epi<1, 1>(epi, grid, mAh, mAl, mBh, mBl, g);
         }
         launch_check();
@@ -1013,12 +1013,19 @@ public:
         if (Tmax > 0) {
             const size_t row_budget = 160 * 1024;                                  // rows per chunk (bounds the activations to a few GB)
             int Tc = (int)std::max<size_t>(1, std::min<size_t>((size_t)Tmax, row_budget / (size_t)B));
+            // Search under the encoder: in the small-batch regime the scan occupies H / 8 SMs and is a latency chain; the search of time
+            // chunk c (CTA pairs, 8 sessions each) runs on the SMs it leaves free while the encoder works on chunk c + 1. Only the last
+            // chunk's search is exposed. The persistent GEMM grids are sized for the SMs that remain.
+            const int ovl_pairs = (B + k::GP_MAX_S - 1) / k::GP_MAX_S;
+            const bool ovl = eager && overlap_search && pair_greedy && fast_greedy && !want_tap && npass && scan4 && scan3 && B <= 64 && Tmax >= 32 * overlap_chunks &&
+                             d.H / scan3::UNITS + 2 * ovl_pairs <= num_sms;
+            if (ovl) Tc = std::min(Tc, (Tmax + overlap_chunks - 1) / overlap_chunks);
             const size_t Mc = (size_t)Tc * B;
             const int L = d.L, D = d.D, H = d.H, F = d.F, J = d.J, KE = d.C3 * d.F3;
             b_xe.ensure(sizeof(float) * Mc * KE); b_x.ensure(sizeof(float) * Mc * D); b_x1.ensure(sizeof(float) * Mc * D); b_x2.ensure(sizeof(float) * Mc * D);
             b_g.ensure(sizeof(float) * Mc * 4 * H); b_hout.ensure(sizeof(float) * Mc * D); b_f1.ensure(sizeof(float) * Mc * F);
             b_m.ensure(sizeof(float) * (size_t)B * H); b_hw.ensure(sizeof(float) * (size_t)L * B * D); b_cw.ensure(sizeof(float) * (size_t)L * B * H);
-            b_eo.ensure(sizeof(float) * Mc * J);
+            b_eo.ensure(sizeof(float) * Mc * J * (ovl ? 2 : 1));          // double-buffered when the search trails the encoder by a chunk
             const bool use_s4 = npass && scan4;
             if (use_s4) { mall_rows = Mc + (size_t)B; b_mall.ensure(sizeof(__half) * 2 * mall_rows * H); }
             b_mw.ensure(sizeof(float) * (size_t)L * B * H);
@@ -1041,9 +1048,12 @@ public:
             float* Mw = b_mw.as<float>();
             if (use_s4) { k::state_gather_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
             const size_t greedy_smem = sizeof(float) * (size_t)(3 * J + d.E);
-            for (int t0 = 0; t0 < Tmax; t0 += Tc) {
+            std::vector<cudaEvent_t> ev_search;                                   // per chunk: its search has finished (overlap mode)
+            float* const EO_base = EO;
+            for (int t0 = 0, ci = 0; t0 < Tmax; t0 += Tc, ci++) {
                 const int tc = std::min(Tc, Tmax - t0);
                 const int M = tc * B;
+                if (ovl) EO = EO_base + (size_t)(ci & 1) * Mc * J;
                 const unsigned ew_grid = (unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, (size_t)num_sms * 8);
                 if (npass == 0) {
                     k::conv_embed_kernel<<<dim3((unsigned)B, (unsigned)tc), 256, conv_smem(), st>>>(cp, FB, row_pitch, d_nsteps, t0, B, Xe); launch_check();
@@ -1094,9 +1104,36 @@ public:
                         tc::basic_norm_split_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(X2, X, X_h, X_l, M, D, w.norm_eps); launch_check();
                     }
                 }
+                if (ovl && ci >= 2) CK(cudaStreamWaitEvent(st, ev_search[(size_t)ci - 2], 0));   // this chunk's encoder rows overwrite the buffer searched two chunks ago
                 if (npass == 0) gemm(k::EPI_BIAS, X, enc_proj_w, enc_proj_b, nullptr, EO, M, J, D);
                 else gemm_tc(tc::GE_F32, X_h, X_l, tw_proj, enc_proj_b, nullptr, EO, nullptr, nullptr, M);
                 const int last = (t0 + tc >= Tmax) ? 1 : 0;
+                if (ovl) {
+                    cudaEvent_t e_enc = ev_get(), e_done = ev_get();
+                    CK(cudaEventRecord(e_enc, st));
+                    CK(cudaStreamWaitEvent(st2, e_enc, 0));
+                    span_begin(2, st2);
+                    const int npair = (B + k::GP_MAX_S - 1) / k::GP_MAX_S;
+                    if (!last) {
+                        // 8 sessions per CTA pair: as few SMs as possible
+                        k::greedy_pair_kernel<<<npair * 2, k::GP_THREADS, gp_smem, st2>>>(jp, dtab, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate,
+                                                                                           b_rec.as<k::DecisionRecord>(), b_np.as<int>(), nullptr, last, tc, k::GP_MAX_S, gp_Rh);
+                    } else {
+                        // the last chunk's search is exposed and has the GPU to itself: the 8-CTA clusters are the faster kernel at this size
+                        const int maxc = std::max(1, num_sms / k::GC_CLUSTER);
+                        const int S = std::min(k::GC_MAX_S, std::max(1, (B + maxc - 1) / maxc));
+                        const int ncl = (B + S - 1) / S;
+                        k::greedy_cluster_kernel<<<ncl * k::GC_CLUSTER, 256, gr_smem, st2>>>(jp, dtab, EO, d_nsteps, d_slot, d_flush, B, Tmax, t0, stride_ms(), gstate,
+                                                                                             b_rec.as<k::DecisionRecord>(), b_np.as<int>(), nullptr, last, tc, S, gr_R);
+                    }
+                    launch_check();
+                    span_end(st2);
+                    CK(cudaEventRecord(e_done, st2));
+                    ev_search.push_back(e_done); ev_pool.push_back(e_enc);       // (an event may be re-recorded once the waits on it are enqueued)
+                    sm_budget = last ? num_sms : ((num_sms - 2 * npair) & ~1);  // GEMMs of the next chunk: the SMs the search does not hold
+                    if (last) CK(cudaStreamWaitEvent(st, e_done, 0));
+                    continue;
+                }
                 span_begin(2);
                 if (fast_greedy && pair_greedy && B >= pair_greedy_min) {
                     const int maxp = std::max(1, num_sms / 2);
@@ -1118,6 +1155,8 @@ public:
                 span_end();
                 if (want_tap) { CK(cudaMemcpyAsync(p_eo.as<float>() + (size_t)t0 * B * J, EO, sizeof(float) * (size_t)M * J, cudaMemcpyDeviceToHost, st)); stat.d2h_bytes += sizeof(float) * (size_t)M * J; }
             }
+            sm_budget = num_sms;
+            for (cudaEvent_t e : ev_search) ev_pool.push_back(e);
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
             if (use_s4) { k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }

@@ -113,7 +113,7 @@ template <int CS, int MMAW> struct Cfg {
 
 // grid = H / 8 CTAs in clusters of CS (launch attribute), cooperative (all CTAs co-resident: they spin on each other's counters)
 template <int CS, int MMAW>
-__global__ void __launch_bounds__(Cfg<CS, MMAW>::THREADS, 1)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(Cfg<CS, MMAW>::THREADS, 1)
 lstm_scan4_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 * NC, H / CS] fp16: per CTA [hi rows ; lo rows], box {64, NC}
                   const __grid_constant__ CUtensorMap mapMhi,   // 2-D [(T + 1) * Bs, H] fp16, box {64, Bp}
                   const __grid_constant__ CUtensorMap mapMlo,

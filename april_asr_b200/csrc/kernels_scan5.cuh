@@ -53,8 +53,8 @@ static inline size_t smem_bytes(int H) { return 1024 + (size_t)H * 128 + (size_t
 
 #define TRACE5(slot_) do { if (a.trace && g == 0) a.trace[((size_t)blockIdx.x * a.T + t) * 8 + (slot_)] = gtimer(); } while (0)
 
-// grid = H / 8 CTAs in clusters of 4 (launch attribute)
-__global__ void __launch_bounds__(THREADS, 1)
+// grid = H / 8 CTAs in clusters of 4 (compile-time cluster dims: ncu cannot replay a launch that carries both the cluster and the cooperative attribute)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_scan5_kernel(const __grid_constant__ CUtensorMap mapW,     // 2-D [GC * 2 * 64, H / 2] fp16: per CTA [hi rows ; lo rows], box {64, 64}
                   const __grid_constant__ CUtensorMap mapMhi,   // 2-D [(T + 1) * Bs, H] fp16, box {64, 128}
                   const __grid_constant__ CUtensorMap mapMlo,

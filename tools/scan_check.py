@@ -15,7 +15,7 @@ def child(a):
     import common as C
     path = C.model_path(a.model)
     pcms = [C.gen_stream(700 + i, int(16000 * a.seconds) + (977 * i if a.ragged else 0)) for i in range(a.sessions)]
-    cols = C.run_product_batch(path, pcms, tap=True, chunk=a.chunk or None)
+    cols = C.run_product_batch(path, pcms, tap=bool(a.tap), chunk=a.chunk or None)
     out = {}
     for i, c in enumerate(cols):
         out["enc%d" % i] = np.stack(c.enc) if c.enc else np.zeros((0, 1), np.float32)
@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--a", default="APRIL_B200_SCAN=simt", help="space-separated VAR=VALUE list of arm A")
     ap.add_argument("--b", default="", help="arm B")
     ap.add_argument("--oracle", type=int, default=0, help="also run the first N sessions through the oracle")
+    ap.add_argument("--tap", type=int, default=1, help="0: compare callback logs only (the taps switch some engine paths off)")
     ap.add_argument("--child", default=None)
     a = ap.parse_args()
     if a.child:
@@ -46,7 +47,7 @@ def main():
             k, v = kv.split("=", 1); env[k] = v
         f = tempfile.mktemp(suffix=".npz")
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--model", a.model, "--sessions", str(a.sessions), "--seconds", str(a.seconds),
-                            "--ragged", str(a.ragged), "--chunk", str(a.chunk), "--child", f], env=env, capture_output=True, text=True, timeout=900)
+                            "--ragged", str(a.ragged), "--chunk", str(a.chunk), "--tap", str(a.tap), "--child", f], env=env, capture_output=True, text=True, timeout=900)
         if r.returncode != 0:
             print("arm %s (%s) FAILED rc=%d\n%s" % (arm, envs, r.returncode, (r.stdout + r.stderr)[-1500:]))
             res[arm] = None
