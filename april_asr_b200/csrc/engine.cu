@@ -161,8 +161,8 @@ public:
     int num_sms = 148;
     int sm_budget = 148;              // SMs the persistent GEMM grids may count on: num_sms minus those lent to the search kernel running beside the encoder
     cudaStream_t st2 = nullptr;       // the search of time chunk c runs here, under the encoder of chunk c + 1 (run_pass)
-    bool overlap_search = false;      // APRIL_B200_OVERLAP
-    int overlap_chunks = 4;
+    bool overlap_search = true;       // APRIL_B200_OVERLAP=0 switches it off, =N (>= 2) sets the number of time chunks
+    int overlap_chunks = 3;           // measured at 64 x 30 s (profiles/r02k): 105.5 ms without, 96.1 / 94.6 / 95.6 / 97.2 ms with 2 / 3 / 4 / 5 halving chunks
     cudaStream_t st = nullptr;
     std::mutex mu;
     EngineStats stat;
@@ -272,7 +272,7 @@ public:
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         num_sms = prop.multiProcessorCount; sm_budget = num_sms;
         { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, hi)); }   // its few CTAs are placed before the encoder's next kernel fills the GPU
-        if (const char* o = getenv("APRIL_B200_OVERLAP")) { overlap_search = atoi(o) > 0; if (atoi(o) > 1) overlap_chunks = atoi(o); }
+        if (const char* o = getenv("APRIL_B200_OVERLAP")) { overlap_search = atoi(o) > 0; if (atoi(o) > 1) overlap_chunks = std::min(atoi(o), 8); }
         profile = getenv("APRIL_B200_TIMING") != nullptr;
         if (d.D % 16 || d.H % 16 || d.F % 16 || d.J % 16 || (d.C3 * d.F3) % 16) { err = "model dims must be multiples of 16"; return false; }
 
@@ -1017,9 +1017,26 @@ public:
             // chunk c (CTA pairs, 8 sessions each) runs on the SMs it leaves free while the encoder works on chunk c + 1. Only the last
             // chunk's search is exposed. The persistent GEMM grids are sized for the SMs that remain.
             const int ovl_pairs = (B + k::GP_MAX_S - 1) / k::GP_MAX_S;
-            const bool ovl = eager && overlap_search && pair_greedy && fast_greedy && !want_tap && npass && scan4 && scan3 && B <= 64 && Tmax >= 32 * overlap_chunks &&
-                             d.H / scan3::UNITS + 2 * ovl_pairs <= num_sms;
-            if (ovl) Tc = std::min(Tc, (Tmax + overlap_chunks - 1) / overlap_chunks);
+            int ovl_n = overlap_chunks;                                           // fewer chunks for shorter passes: the last one keeps >= 24 steps
+            while (ovl_n >= 2 && Tmax < 24 * ((1 << ovl_n) - 1)) ovl_n--;
+            const bool ovl = eager && overlap_search && pair_greedy && fast_greedy && !want_tap && npass && scan4 && scan3 && B >= 24 && B <= 64 && ovl_n >= 2 &&   // below ~24 sessions the search is too short to be worth the chunking (8 sessions: 69.0 vs 65.6 ms)
+                            
+                             (size_t)Tmax * (size_t)B <= row_budget && d.H / scan3::UNITS + 2 * ovl_pairs <= num_sms;
+            // chunk lengths: uniform without overlap; with it, halving (8 : 4 : 2 : 1 ...): the search of a chunk runs ~2.5x slower on its
+            // few SMs than the encoder of the same steps on the rest, so each chunk's search must fit under the encoder of ALL later
+            // chunks, and the last chunk (whose search is exposed) should be short
+            std::vector<int> chunk_len;
+            if (ovl) {
+                const int n = ovl_n, wsum = (1 << n) - 1;
+                for (int c = 0, left = Tmax; c < n; c++) {
+                    const int len = c == n - 1 ? left : std::min(left, std::max(1, (int)(((long long)Tmax * (1 << (n - 1 - c)) + wsum / 2) / wsum)));
+                    if (len > 0) chunk_len.push_back(len);
+                    left -= len;
+                }
+                Tc = 0; for (int len : chunk_len) Tc = std::max(Tc, len);
+            } else {
+                for (int t0 = 0; t0 < Tmax; t0 += Tc) chunk_len.push_back(std::min(Tc, Tmax - t0));
+            }
             const size_t Mc = (size_t)Tc * B;
             const int L = d.L, D = d.D, H = d.H, F = d.F, J = d.J, KE = d.C3 * d.F3;
             b_xe.ensure(sizeof(float) * Mc * KE); b_x.ensure(sizeof(float) * Mc * D); b_x1.ensure(sizeof(float) * Mc * D); b_x2.ensure(sizeof(float) * Mc * D);
@@ -1050,8 +1067,8 @@ public:
             const size_t greedy_smem = sizeof(float) * (size_t)(3 * J + d.E);
             std::vector<cudaEvent_t> ev_search;                                   // per chunk: its search has finished (overlap mode)
             float* const EO_base = EO;
-            for (int t0 = 0, ci = 0; t0 < Tmax; t0 += Tc, ci++) {
-                const int tc = std::min(Tc, Tmax - t0);
+            for (int t0 = 0, ci = 0; ci < (int)chunk_len.size(); t0 += chunk_len[(size_t)ci], ci++) {
+                const int tc = chunk_len[(size_t)ci];
                 const int M = tc * B;
                 if (ovl) EO = EO_base + (size_t)(ci & 1) * Mc * J;
                 const unsigned ew_grid = (unsigned)std::min<size_t>(((size_t)M * D / 4 + 255) / 256, (size_t)num_sms * 8);

@@ -431,6 +431,8 @@ def main():
             "x_realtime_per_stream": a.seconds / (compute_s / a.steps),
             "e2e": {"value": frames_total / wall_s, "unit": "frames/s", "ms_per_step": 1000.0 * wall_s / a.steps,
                     "h2d_bytes_per_step": st.h2d_bytes / a.steps, "d2h_bytes_per_step": st.d2h_bytes / a.steps,
+                    "of_which_upload_ms": (st.device_ms - st.compute_ms) / a.steps,      # pinned staging + H2D before the first kernel (this rank)
+                    "of_which_host_ms": 1000.0 * sum(r["walls"]) / a.steps - st.device_ms / a.steps,   # planning, result replay, callbacks (this rank)
                     "x_realtime_per_stream": a.seconds / (wall_s / a.steps)},
             "gpu_launches": int(st.kernel_launches), "model_load_s": t_load,
             "clocks": r["clocks"],

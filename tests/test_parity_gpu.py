@@ -308,3 +308,26 @@ def test_fp32_simt_tier_is_a_tight_device_side_reference():
     print("fp32 SIMT tier vs oracle:", res)
     assert res["same"] and res["passes"] and res["steps"] > 50
     assert res["enc"] < 5e-5 and res["logits"] < 5e-5
+
+
+@pytest.mark.parametrize("env", [{"APRIL_B200_GREEDY": "pair"}, {"APRIL_B200_GREEDY": "cluster", "APRIL_B200_OVERLAP": "0"},
+                                 {"APRIL_B200_OVERLAP": "4"}, {"APRIL_B200_OVERLAP": "7", "APRIL_B200_GREEDY": "pair"}],
+                         ids=["search-on-cta-pairs", "search-on-8-cta-clusters", "search-under-the-encoder-4-chunks", "search-under-the-encoder-7-chunks"])
+def test_every_search_schedule_matches_the_oracle(env):
+    """The engine has two search kernels (8-CTA clusters with the joiner in registers; CTA pairs streaming it from L2) and two
+    schedules (search after the encoder; search of time chunk c under the encoder of chunk c + 1). Whatever the defaults pick for a
+    batch size, each combination is held to the oracle's callbacks here: 28 ragged sessions x ~20 s in one feed + flush (mid model),
+    and a second feed afterwards so that the state a schedule leaves behind is exercised too. The switches are read at model load."""
+    import os
+    path = C.model_path("mid")
+    pcms = [C.gen_stream(2100 + i, 16000 * 20 + 3111 * i) for i in range(28)]          # the overlapped schedule serves 24..64 sessions
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got = C.run_product_batch(path, pcms, chunk=16000 * 14)          # two feeds: 14 s, then the rest
+    finally:
+        for k, v in saved.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+    want = _oracle_many(path, pcms, chunk=16000 * 14)
+    C.check_streams(path, pcms, got, want, list(range(28)), "search schedule %s" % env, chunk=16000 * 14)
