@@ -350,7 +350,9 @@ def main():
                 "latency_note": "per chunk and stream: aas_feed_pcm16 returned - entered; a synchronous session's handler runs before the call returns",
                 "tick_ms": {"p50": q(per_tick, 0.5), "p99": q(per_tick, 0.99)},
                 "x_realtime_per_stream": 40.0 / q(per_tick, 0.5), "frames_per_sec": S * 4 / (float(per_tick.mean()) / 1e3),
-                "device_passes": int(st.passes), "mean_sessions_per_pass": st.pass_sessions / max(1, st.passes), "callbacks": cnt}
+                "device_passes": int(st.passes), "mean_sessions_per_pass": st.pass_sessions / max(1, st.passes),
+                "device_ms_per_pass": st.device_ms / max(1, st.passes), "of_which_after_upload_ms": st.compute_ms / max(1, st.passes),   # CUDA events on the engine stream: the rest of a chunk's latency is host (coalescing window, planning, staging, wake-ups, callbacks)
+                "callbacks": cnt}
 
     if a.mode == "stream":
         sb = stream_block(a.sessions if a.sessions != 64 else 256, a.ticks)
