@@ -1,6 +1,7 @@
 #!/bin/bash
 # Profiling pass on the GPU box (see /opt/skills/guides/B200_PROFILING.md): launch list of the default bench command + one `--set full`
-# capture per hot kernel. Numbers printed by bench.py under ncu are NOT bench values.
+# capture per hot kernel. Numbers printed by bench.py under ncu are NOT bench values. (The scan kernels carry their cluster dims at compile
+# time: ncu cannot replay a launch that has BOTH the cluster-dimension and the cooperative launch attribute — LaunchFailed on pass 2.)
 set -u
 OUT=gpurun_out/prof; mkdir -p $OUT
 BENCH="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extra"
@@ -15,6 +16,7 @@ cap scan4_b200 lstm_scan4_kernel 0 "--sessions 200"
 cap scan5_b512 lstm_scan5_kernel 0 "--sessions 512"
 cap gemm_wih "gemm_tc_kernel<.int.3, .int.0, .int.2>" 1 ""
 cap greedy greedy_cluster_kernel 0 ""
+cap greedy_pair_b512 greedy_pair_kernel 0 "--sessions 512"
 cap fbank512 fbank512_kernel 0 ""
 cap conv12 conv12_im2col_kernel 0 ""
 ls -la $OUT | grep -v ncu-rep
