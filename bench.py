@@ -79,18 +79,33 @@ def ncu_traffic(kernel_substr):
 
 
 class ClockSampler:
+    """`nvidia-smi -lms 50` running in the background from before the warm-up (its start-up alone can take longer than a short timed
+    region); every row carries nvidia-smi's own timestamp and only the rows inside [begin(), end()] — the timed region — are used."""
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.t0 = self.t1 = None
+        q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(gpu_index), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is None:
+            self.end()
+        time.sleep(0.12)                                   # let the sample that straddles end() be written
         self.p.terminate()
         try:
             self.p.wait(timeout=3)
@@ -99,19 +114,26 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, total = [], None, set(), 0
+        slack = datetime.timedelta(milliseconds=30)
         for r in rows:
-            if len(r) < 9 or r[0] != str(self.idx):
+            if len(r) < 10 or r[1] != str(self.idx):
                 continue
             try:
-                sm.append(float(r[1])); mx = float(r[2])
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                clk, cmax = float(r[2]), float(r[3])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+            total += 1
+            if self.t0 is not None and not (self.t0 - slack <= ts <= self.t1 + slack):
+                continue
+            sm.append(clk); mx = cmax
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
         busy = [x for x in sm if mx and x > 0.3 * mx] or sm
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "sampling": "nvidia-smi -lms 50, rows time-stamped inside the timed region (%d rows over the whole run)" % total}
 
 
 def ensure_model(rank, dist):
@@ -285,6 +307,7 @@ def main():
             for h in ss:
                 lib.c.aas_free(h)
             return dt
+        sampler = ClockSampler(local) if rank == 0 else None
         for _ in range(warmup):
             one_step()
         st = _ffi.AprilB200Stats()
@@ -295,9 +318,10 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler: sampler.begin()
         walls = [one_step() for _ in range(steps)]
         torch.cuda.synchronize()
+        if sampler: sampler.end()
         if dist is not None:
             dist.barrier()
         clocks = sampler.stop() if sampler else None
