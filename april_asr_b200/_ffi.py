@@ -49,7 +49,7 @@ REFERENCE_SYMBOLS = [
     "aas_realtime_get_speedup", "aas_free",
 ]
 B200_SYMBOLS = [
-    "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_session_device", "aab_get_stats",
+    "aab_feed_pcm16_batch", "aab_flush_batch", "aab_device_count", "aab_set_device", "aab_session_device", "aab_pin_host_memory", "aab_unpin_host_memory", "aab_get_stats",
     "aab_set_tap", "aab_engine_version", "aab_debug_fbank", "aab_set_timing", "aab_counting_handler", "aab_debug_gemm", "aab_debug_replay", "aab_debug_plan", "aab_debug_model_digest",
 ]
 
@@ -83,6 +83,8 @@ class Lib:
             c.aab_device_count.argtypes, c.aab_device_count.restype = [], ctypes.c_int
             c.aab_set_device.argtypes, c.aab_set_device.restype = [ctypes.c_int], ctypes.c_int
             c.aab_session_device.argtypes, c.aab_session_device.restype = [ctypes.c_void_p], ctypes.c_int
+            c.aab_pin_host_memory.argtypes, c.aab_pin_host_memory.restype = [ctypes.c_void_p, ctypes.c_size_t], ctypes.c_int
+            c.aab_unpin_host_memory.argtypes, c.aab_unpin_host_memory.restype = [ctypes.c_void_p], ctypes.c_int
             c.aab_engine_version.argtypes, c.aab_engine_version.restype = [], cp
             c.aab_debug_fbank.argtypes = [vp, ctypes.POINTER(ctypes.c_short), sz, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
             c.aab_debug_fbank.restype = ctypes.c_int

@@ -483,6 +483,8 @@ APRIL_EXPORT int aab_flush_batch(AprilASRSession* sessions, size_t n) {
 }
 
 APRIL_EXPORT int aab_session_device(AprilASRSession session) { return session ? session->lane->engine->device() : -1; }
+APRIL_EXPORT int aab_pin_host_memory(void* ptr, size_t bytes) { return (ptr && bytes) ? host_pin(ptr, bytes) : -1; }
+APRIL_EXPORT int aab_unpin_host_memory(void* ptr) { return ptr ? host_unpin(ptr) : -1; }
 
 APRIL_EXPORT int aab_get_stats(AprilASRModel model, AprilB200Stats* out, int reset) {
     if (!model || !out) return -1;

@@ -934,7 +934,35 @@ public:
         cudaEvent_t ev0 = ev_get(), ev1 = ev_get(), evc = ev_get();
         bool pcm_uploaded = false;
         const int n_stage = (pcm_total * sizeof(int16_t) >= ((size_t)8 << 20)) ? std::min(B, 8) : 1;
-        if (n_stage > 1) {
+        // Caller-pinned audio (aab_pin_host_memory, or any buffer page-locked for CUDA): no staging copy at all. The few hundred tail
+        // samples of a session go through the pinned staging buffer, its new samples are DMA'd straight from the caller's memory.
+        bool all_pinned = n_stage > 1;
+        for (int b = 0; b < B && all_pinned; b++) {
+            const PassItem& it = items[(size_t)b];
+            if (it.flush || it.count == 0) continue;
+            cudaPointerAttributes pa{};
+            if (cudaPointerGetAttributes(&pa, it.pcm) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); all_pinned = false; }
+        }
+        if (all_pinned) {
+            b_pcm.ensure(pcm_total * sizeof(int16_t));
+            CK(cudaEventRecord(ev0, st));
+            int16_t* dp = b_pcm.as<int16_t>();
+            for (int b = 0; b < B; b++) {
+                PassItem& it = items[(size_t)b];
+                StreamFraming& fr = *it.fr;
+                const size_t off = (size_t)meta[(size_t)b].pcm_off, nt = fr.tail.size(), n_in = it.flush ? (size_t)FLUSH_ZEROS : it.count, n_buf = nt + n_in;
+                if (nt) { memcpy(hp + off, fr.tail.data(), nt * sizeof(int16_t)); CK(cudaMemcpyAsync(dp + off, hp + off, nt * sizeof(int16_t), cudaMemcpyHostToDevice, st)); }
+                if (it.flush) CK(cudaMemsetAsync(dp + off + nt, 0, n_in * sizeof(int16_t), st));
+                else if (n_in) CK(cudaMemcpyAsync(dp + off + nt, it.pcm, n_in * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+                size_t consumed = (size_t)meta[(size_t)b].n_frames * (size_t)shift;     // next frame starts here (fbank.c:198-224)
+                if (consumed > n_buf) consumed = n_buf;
+                std::vector<int16_t> rest; rest.reserve(n_buf - consumed);
+                for (size_t i = consumed; i < n_buf; i++) rest.push_back(i < nt ? hp[off + i] : (it.flush ? (int16_t)0 : it.pcm[i - nt]));
+                fr.tail.swap(rest);
+            }
+            stat.h2d_bytes += pcm_total * sizeof(int16_t);
+            pcm_uploaded = true;
+        } else if (n_stage > 1) {
             b_pcm.ensure(pcm_total * sizeof(int16_t));
             CK(cudaEventRecord(ev0, st));
             const int nblk = std::min(B, 8);
@@ -1284,6 +1312,15 @@ Engine* Engine::create(const LoadedModel& m, int device, std::string& err) {
     EngineImpl* e = new EngineImpl();
     if (!e->init(m, device, err)) { delete e; return nullptr; }
     return e;
+}
+
+int host_pin(void* p, size_t bytes) {
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+int host_unpin(void* p) {
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
 }
 
 std::vector<int> cuda_devices_sm100() {

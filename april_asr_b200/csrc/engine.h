@@ -72,5 +72,7 @@ public:
 };
 
 std::vector<int> cuda_devices_sm100();     // CUDA ordinals of the usable sm_100 devices, in ordinal order
+int host_pin(void* p, size_t bytes);       // cudaHostRegister (portable across the GPUs of the process) / cudaHostUnregister; 0 = ok
+int host_unpin(void* p);
 
 }  // namespace april

@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--soak-minutes", type=float, default=60.0, help="audio minutes per session in --mode soak")
     ap.add_argument("--soak-chunk", type=float, default=10.0, help="audio seconds per feed call in --mode soak")
     ap.add_argument("--ticks", type=int, default=250)
+    ap.add_argument("--no-pin", action="store_true", help="leave the input PCM buffers pageable (the library stages them into pinned memory itself)")
     ap.add_argument("--lanes", type=int, default=0, help="ONE process driving this many GPUs through the library's own placement (SURVEY.md par. 8e): sessions x lanes streams, no torchrun; 0 = one process per GPU")
     a = ap.parse_args()
 
@@ -284,6 +285,10 @@ def main():
         """warmup + steps passes of S fresh sessions x seconds; returns the per-config measurements (this rank's)."""
         n = int(16000 * seconds)
         pcms = gen_streams(stream_ids, n)
+        # the step's inputs live in PINNED host memory (page-locked once, outside the timed region, through the library's own call):
+        # the H2D copies inside the timed region are DMA'd straight from these buffers. --no-pin leaves them pageable: the library then
+        # copies every feed into its pinned staging buffer first.
+        pinned = [p for p in pcms if not a.no_pin and lib.c.aab_pin_host_memory(ctypes.c_void_p(p.ctypes.data), p.nbytes) == 0]
         counters = (ctypes.c_uint64 * 4)()
         hs_t = ctypes.c_void_p * S
         ptrs = (ctypes.POINTER(ctypes.c_short) * S)(*[p.ctypes.data_as(ctypes.POINTER(ctypes.c_short)) for p in pcms])
@@ -325,9 +330,11 @@ def main():
         if dist is not None:
             dist.barrier()
         clocks = sampler.stop() if sampler else None
+        for p in pinned:
+            lib.c.aab_unpin_host_memory(ctypes.c_void_p(p.ctypes.data))
         lib.c.aab_get_stats(m.handle, ctypes.byref(st), 1)
         lib.c.aab_set_timing(m.handle, 0)
-        return {"S": S, "n": n, "walls": walls, "st": st, "clocks": clocks, "counters": [int(x) for x in counters]}
+        return {"S": S, "n": n, "walls": walls, "st": st, "clocks": clocks, "counters": [int(x) for x in counters], "pinned_inputs": len(pinned) == len(pcms)}
 
     def roofline_of(r, steps):
         st = r["st"]
@@ -453,7 +460,8 @@ def main():
             "config": {"workload": workload, "sessions_per_gpu": a.sessions, "seconds_per_session": a.seconds,
                        "parallelism": "sessions sharded, %d per GPU, no collective on the data path" % a.sessions,
                        "l2": "working set (337 MB fp32 weights + GBs of activations per pass) exceeds the 126 MB L2; no explicit flush",
-                       "timing": "value: device-resident part of each pass (CUDA events on the engine stream, after the PCM upload), max over ranks; e2e: wall clock around the C-ABI calls with host buffers (staging, H2D, compute, D2H, callbacks)"},
+                       "timing": "value: device-resident part of each pass (CUDA events on the engine stream, after the PCM upload), max over ranks; e2e: wall clock around the C-ABI calls with host buffers (H2D of the inputs, compute, D2H of the decisions, result replay, callbacks)",
+                       "inputs": "pinned host memory (aab_pin_host_memory once per buffer, outside the timed region): DMA straight from the caller's buffers" if r["pinned_inputs"] else "pageable host memory: the library copies each feed into its pinned staging buffer, then H2D"},
             "x_realtime_per_stream": a.seconds / (compute_s / a.steps),
             "e2e": {"value": frames_total / wall_s, "unit": "frames/s", "ms_per_step": 1000.0 * wall_s / a.steps,
                     "h2d_bytes_per_step": st.h2d_bytes / a.steps, "d2h_bytes_per_step": st.d2h_bytes / a.steps,

@@ -45,6 +45,13 @@ APRIL_EXPORT int aab_set_device(int device);
 /* CUDA ordinal of the GPU a session was placed on. */
 APRIL_EXPORT int aab_session_device(AprilASRSession session);
 
+/* Optional: page-lock a long-lived audio buffer of the caller (a capture ring, a decoded file) so that batched feeds are DMA'd
+ * straight out of it. Without it the library copies every feed into its own pinned staging buffer first (the largest host cost of
+ * a big pass). Any memory that is already page-locked for CUDA (cudaHostAlloc / cudaHostRegister) is recognised too. Returns 0 on
+ * success. The range must stay registered while a feed call that reads from it is in progress; unpin before freeing it. */
+APRIL_EXPORT int aab_pin_host_memory(void* ptr, size_t bytes);
+APRIL_EXPORT int aab_unpin_host_memory(void* ptr);
+
 typedef struct AprilB200Stats {
     uint64_t encoder_steps;     /* session-steps run through the encoder */
     uint64_t joiner_passes;     /* joiner evaluations (1..3 per session-step) */
