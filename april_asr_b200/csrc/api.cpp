@@ -13,6 +13,7 @@
 #include <mutex>
 #include <set>
 #include <thread>
+#include <functional>
 #include <vector>
 
 #include "../../include/april_b200.h"
@@ -104,9 +105,9 @@ struct AprilASRSession_i {
 };
 
 // ---------------------------------------------------------------------------------------------
-static void replay(AprilASRSession_i* s, PassItem& it, bool flush) {
+static void replay_steps(AprilASRSession_i* s, PassItem& it, int t_from, int t_to) {
     const size_t stride = (size_t)s->lane->engine->stride_ms();
-    for (int t = 0; t < it.n_steps; t++) {
+    for (int t = t_from; t < t_to; t++) {
         s->shaper->begin_step(stride);
         const int np = it.npass[(size_t)t];
         for (int p = 0; p < np; p++) {
@@ -118,6 +119,11 @@ static void replay(AprilASRSession_i* s, PassItem& it, bool flush) {
             }
         }
     }
+}
+// what the pass decided for this session, in stream order (steps an early-steps listener has already replayed are skipped)
+static void replay(AprilASRSession_i* s, PassItem& it, bool flush) {
+    replay_steps(s, it, it.delivered, it.n_steps);
+    it.delivered = it.n_steps;
     if (flush) s->shaper->on_flush_end();
 }
 
@@ -126,7 +132,19 @@ static void run_items(std::vector<AprilASRSession_i*>& ss, std::vector<PassItem>
     if (ss.empty()) return;
     bool one_lane = true;
     for (auto* s : ss) if (s->lane != ss[0]->lane) { one_lane = false; break; }
-    if (one_lane) ss[0]->lane->engine->run_pass(items);
+    if (one_lane) {
+        // Big passes are computed in time chunks; the callbacks of a finished chunk run here, on the calling thread, while the device
+        // works on the next one (the result replay is ~3 ms of a 64 x 30 s pass). Order: per session as always; across the sessions
+        // of the call chunk by chunk, then session by session. The handlers run while the engine is locked: from THIS entry point
+        // (aab_*_batch, an addition of this library) they must not call back into the library.
+        const std::function<void(int, int)> early = [&](int, int t1) {
+            for (size_t i = 0; i < ss.size(); i++) {
+                const int upto = std::min(t1, items[i].n_steps);
+                if (upto > items[i].delivered) { replay_steps(ss[i], items[i], items[i].delivered, upto); items[i].delivered = upto; }
+            }
+        };
+        ss[0]->lane->engine->run_pass(items, &early);
+    }
     else {
         std::vector<Lane*> lanes;
         for (auto* s : ss) if (std::find(lanes.begin(), lanes.end(), s->lane) == lanes.end()) lanes.push_back(s->lane);

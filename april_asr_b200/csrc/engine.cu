@@ -873,7 +873,7 @@ public:
         return ms;
     }
 
-    void run_pass(std::vector<PassItem>& items) override {
+    void run_pass(std::vector<PassItem>& items, const std::function<void(int, int)>* early) override {
         std::lock_guard<std::mutex> lk(mu);
         const int B = (int)items.size();
         if (B == 0) return;
@@ -1003,6 +1003,9 @@ public:
         const bool want_tap = tap != nullptr;
         bool any_flush_k = false;
         for (int b = 0; b < B; b++) any_flush_k |= items[(size_t)b].flush;
+        struct EarlySteps { cudaEvent_t ev; int t0, t1; };
+        std::vector<EarlySteps> early_steps;        // time chunks whose decisions reach the host while later chunks are still computed
+        int early_until = 0;                        // steps [0, early_until) are copied chunk by chunk; the final copy takes the rest
         // everything from the uploads to the result copies is enqueued by this lambda: eagerly, or once into a CUDA graph
         auto enqueue = [&](bool eager) {
         if (!pcm_uploaded) {
@@ -1085,6 +1088,7 @@ public:
                    *X1_l = b_x1_l.as<__half>(), *F1_h = b_f1_h.as<__half>(), *F1_l = b_f1_l.as<__half>();
             rec_bytes = sizeof(k::DecisionRecord) * (size_t)B * Tmax * 3; np_bytes = sizeof(int) * (size_t)B * Tmax;
             b_rec.ensure(rec_bytes); b_np.ensure(np_bytes);
+            p_rec.ensure(rec_bytes); p_np.ensure(np_bytes);
             if (want_tap) { b_tap.ensure(sizeof(float) * (size_t)B * Tmax * 3 * d.V); p_tap.ensure(sizeof(float) * (size_t)B * Tmax * 3 * d.V); p_eo.ensure(sizeof(float) * (size_t)Tmax * B * J); }
             float *Xe = b_xe.as<float>(), *X = b_x.as<float>(), *X1 = b_x1.as<float>(), *X2 = b_x2.as<float>(), *G = b_g.as<float>(), *Hout = b_hout.as<float>(),
                   *F1 = b_f1.as<float>(), *Ms = b_m.as<float>(), *Hw = b_hw.as<float>(), *Cw = b_cw.as<float>(), *EO = b_eo.as<float>();
@@ -1175,6 +1179,15 @@ public:
                     span_end(st2);
                     CK(cudaEventRecord(e_done, st2));
                     ev_search.push_back(e_done); ev_pool.push_back(e_enc);       // (an event may be re-recorded once the waits on it are enqueued)
+                    if (early && !last) {                                        // this chunk's decisions go to the host now: [B][Tmax][3] records, [B][Tmax] pass counts
+                        const size_t rp = sizeof(k::DecisionRecord) * 3;
+                        CK(cudaMemcpy2DAsync(p_rec.as<char>() + (size_t)t0 * rp, (size_t)Tmax * rp, b_rec.as<char>() + (size_t)t0 * rp, (size_t)Tmax * rp, (size_t)tc * rp, (size_t)B, cudaMemcpyDeviceToHost, st2));
+                        CK(cudaMemcpy2DAsync(p_np.as<char>() + (size_t)t0 * sizeof(int), (size_t)Tmax * sizeof(int), b_np.as<char>() + (size_t)t0 * sizeof(int), (size_t)Tmax * sizeof(int), (size_t)tc * sizeof(int), (size_t)B, cudaMemcpyDeviceToHost, st2));
+                        cudaEvent_t e_copy = ev_get();
+                        CK(cudaEventRecord(e_copy, st2));
+                        early_steps.push_back(EarlySteps{ e_copy, t0, t0 + tc });
+                        early_until = t0 + tc;
+                    }
                     sm_budget = last ? num_sms : ((num_sms - 2 * npair) & ~1);  // GEMMs of the next chunk: the SMs the search does not hold
                     if (last) CK(cudaStreamWaitEvent(st, e_done, 0));
                     continue;
@@ -1205,9 +1218,14 @@ public:
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(h_store, d_slot, Hw, L, B, D); launch_check();
             k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(c_store, d_slot, Cw, L, B, H); launch_check();
             if (use_s4) { k::state_scatter_kernel<<<dim3((unsigned)B, (unsigned)L), 128, 0, st>>>(m_store, d_slot, Mw, L, B, H); launch_check(); }
-            p_rec.ensure(rec_bytes); p_np.ensure(np_bytes);
-            CK(cudaMemcpyAsync(p_rec.p, b_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(p_np.p, b_np.p, np_bytes, cudaMemcpyDeviceToHost, st));
+            if (early_until == 0) {
+                CK(cudaMemcpyAsync(p_rec.p, b_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(p_np.p, b_np.p, np_bytes, cudaMemcpyDeviceToHost, st));
+            } else {                                                              // the host may be reading the earlier chunks' records: copy only the rest
+                const size_t rp = sizeof(k::DecisionRecord) * 3; const int t0r = early_until, tcr = Tmax - early_until;
+                CK(cudaMemcpy2DAsync(p_rec.as<char>() + (size_t)t0r * rp, (size_t)Tmax * rp, b_rec.as<char>() + (size_t)t0r * rp, (size_t)Tmax * rp, (size_t)tcr * rp, (size_t)B, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpy2DAsync(p_np.as<char>() + (size_t)t0r * sizeof(int), (size_t)Tmax * sizeof(int), b_np.as<char>() + (size_t)t0r * sizeof(int), (size_t)Tmax * sizeof(int), (size_t)tcr * sizeof(int), (size_t)B, cudaMemcpyDeviceToHost, st));
+            }
             stat.d2h_bytes += rec_bytes + np_bytes;
             if (want_tap) { CK(cudaMemcpyAsync(p_tap.p, b_tap.p, sizeof(float) * (size_t)B * Tmax * 3 * d.V, cudaMemcpyDeviceToHost, st)); }
         } else {
@@ -1262,6 +1280,35 @@ public:
             if (!small) pending_key.B = -1;
         }
         CK(cudaEventRecord(ev1, st));
+        // ---- hand decisions back: chunk by chunk while the device works on (overlap mode with a listener), the rest at the end ----
+        const k::DecisionRecord* hr = p_rec.as<k::DecisionRecord>();
+        const int* hn = p_np.as<int>();
+        for (int b = 0; b < B; b++) {
+            PassItem& it = items[(size_t)b];
+            it.npass.assign((size_t)it.n_steps, 0);
+            it.decisions.assign((size_t)it.n_steps * 3, StepDecision{});
+        }
+        auto hand_back = [&](int t_from, int t_to) {
+            for (int b = 0; b < B; b++) {
+                PassItem& it = items[(size_t)b];
+                for (int t = t_from; t < std::min(t_to, it.n_steps); t++) {
+                    int np = hn[(size_t)b * Tmax + t];
+                    it.npass[(size_t)t] = np;
+                    stat.joiner_passes += (uint64_t)np;
+                    for (int p = 0; p < np; p++) {
+                        const k::DecisionRecord& r = hr[((size_t)b * Tmax + t) * 3 + p];
+                        it.decisions[(size_t)t * 3 + p] = StepDecision{ r.max_idx, r.is_blank, r.max_val, r.blank_val };
+                        if (!r.is_blank) stat.decoder_runs++;
+                    }
+                }
+            }
+        };
+        for (const EarlySteps& e : early_steps) {
+            CK(cudaEventSynchronize(e.ev));
+            hand_back(e.t0, e.t1);
+            (*early)(e.t0, e.t1);
+            ev_pool.push_back(e.ev);
+        }
         CK(cudaStreamSynchronize(st));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1271,24 +1318,7 @@ public:
         ev_pool.push_back(ev0); ev_pool.push_back(ev1); ev_pool.push_back(evc);
         spans_collect();
 
-        // ---- hand decisions back ----------------------------------------------------------------------
-        const k::DecisionRecord* hr = p_rec.as<k::DecisionRecord>();
-        const int* hn = p_np.as<int>();
-        for (int b = 0; b < B; b++) {
-            PassItem& it = items[(size_t)b];
-            it.npass.assign((size_t)it.n_steps, 0);
-            it.decisions.assign((size_t)it.n_steps * 3, StepDecision{});
-            for (int t = 0; t < it.n_steps; t++) {
-                int np = hn[(size_t)b * Tmax + t];
-                it.npass[(size_t)t] = np;
-                stat.joiner_passes += (uint64_t)np;
-                for (int p = 0; p < np; p++) {
-                    const k::DecisionRecord& r = hr[((size_t)b * Tmax + t) * 3 + p];
-                    it.decisions[(size_t)t * 3 + p] = StepDecision{ r.max_idx, r.is_blank, r.max_val, r.blank_val };
-                    if (!r.is_blank) stat.decoder_runs++;
-                }
-            }
-        }
+        hand_back(early_until, Tmax);
         if (want_tap && Tmax > 0) {
             const float* eo = p_eo.as<float>();
             const float* lg = p_tap.as<float>();

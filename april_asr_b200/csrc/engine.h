@@ -4,6 +4,7 @@
 // (april_session.c:40-58) and the fbank_* calls (april_session.c:35,441-442,528,552-559).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -40,6 +41,7 @@ struct PassItem {
     int n_steps = 0;
     std::vector<int> npass;                 // [n_steps]
     std::vector<StepDecision> decisions;    // [n_steps][3]
+    int delivered = 0;                      // steps the caller has already consumed through the early-steps callback
 };
 
 struct EngineStats {
@@ -60,7 +62,10 @@ public:
     virtual ~Engine() {}
     virtual int alloc_slot() = 0;           // device-side per-stream state (h, c, context, carry rows); zeros / blanks
     virtual void free_slot(int slot) = 0;
-    virtual void run_pass(std::vector<PassItem>& items) = 0;   // aborts on CUDA errors (ORT_ABORT_ON_ERROR convention)
+    // aborts on CUDA errors (ORT_ABORT_ON_ERROR convention). `early`, if given, is called ON THE CALLING THREAD, WHILE THE ENGINE IS LOCKED
+    // and the device still works on later time chunks, with [t_begin, t_end): the decisions of those steps of every item are final and
+    // stored in the items (steps beyond an item's n_steps do not exist). Steps never announced are simply there when run_pass returns.
+    virtual void run_pass(std::vector<PassItem>& items, const std::function<void(int, int)>* early = nullptr) = 0;
     virtual EngineStats stats(bool reset) = 0;
     virtual void set_tap(TapFn fn, void* userdata) = 0;
     virtual void set_timing(bool on) = 0;

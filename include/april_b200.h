@@ -25,7 +25,11 @@ extern "C" {
 /* Batched aas_feed_pcm16 (replaces N calls of src/april_session.c:479). All sessions must be
  * synchronous sessions of the same model. pcm16[i] may be NULL iff short_count[i] == 0.
  * Returns 0, or -1 on invalid arguments (nothing processed). Device errors abort(), as ORT errors do
- * in the reference (src/ort_util.h:29-38). */
+ * in the reference (src/ort_util.h:29-38).
+ * Handlers run on the calling thread before the call returns, each session's callbacks in stream order. Across the sessions of the
+ * call the order is: time chunk by time chunk (big passes are computed in chunks and the callbacks of a finished chunk are delivered
+ * while the device works on the next), session by session within a chunk. Handlers invoked from the two batch entry points must not
+ * call back into the library (the engine is locked while they run); the reference's own entry points have no such restriction. */
 APRIL_EXPORT int aab_feed_pcm16_batch(AprilASRSession* sessions, short** pcm16,
                                       const size_t* short_count, size_t n_sessions);
 
