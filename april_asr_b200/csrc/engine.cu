@@ -1211,6 +1211,15 @@ public:
                 }
                 launch_check();
                 span_end();
+                if (early && eager && !last && !want_tap) {                      // any multi-chunk pass: this chunk's decisions go to the host now
+                    const size_t rp = sizeof(k::DecisionRecord) * 3;
+                    CK(cudaMemcpy2DAsync(p_rec.as<char>() + (size_t)t0 * rp, (size_t)Tmax * rp, b_rec.as<char>() + (size_t)t0 * rp, (size_t)Tmax * rp, (size_t)tc * rp, (size_t)B, cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpy2DAsync(p_np.as<char>() + (size_t)t0 * sizeof(int), (size_t)Tmax * sizeof(int), b_np.as<char>() + (size_t)t0 * sizeof(int), (size_t)Tmax * sizeof(int), (size_t)tc * sizeof(int), (size_t)B, cudaMemcpyDeviceToHost, st));
+                    cudaEvent_t e_copy = ev_get();
+                    CK(cudaEventRecord(e_copy, st));
+                    early_steps.push_back(EarlySteps{ e_copy, t0, t0 + tc });
+                    early_until = t0 + tc;
+                }
                 if (want_tap) { CK(cudaMemcpyAsync(p_eo.as<float>() + (size_t)t0 * B * J, EO, sizeof(float) * (size_t)M * J, cudaMemcpyDeviceToHost, st)); stat.d2h_bytes += sizeof(float) * (size_t)M * J; }
             }
             sm_budget = num_sms;
