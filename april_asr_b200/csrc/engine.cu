@@ -244,6 +244,8 @@ public:
     k::GreedyState* gstate = nullptr;
 
     // pass buffers
+    DevBuf b_splitk;                  // partial tiles of split-K GEMMs
+    bool splitk_ok = true;            // APRIL_B200_SPLITK=0: dev switch
     DevBuf b_pcm, b_meta, b_fb, b_xe, b_x, b_x1, b_x2, b_g, b_hout, b_f1, b_m, b_hw, b_cw, b_eo, b_rec, b_np, b_tap;
     DevBuf b_nsteps, b_slot, b_carry, b_nnew, b_padb, b_nfr, b_flush, b_keepf, b_nkeep, b_pcmoff;
     PinBuf p_pcm, p_meta, p_rec, p_np, p_eo, p_tap;
@@ -272,6 +274,7 @@ public:
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         num_sms = prop.multiProcessorCount; sm_budget = num_sms;
         { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, hi)); }   // its few CTAs are placed before the encoder's next kernel fills the GPU
+        if (const char* o = getenv("APRIL_B200_SPLITK")) splitk_ok = atoi(o) != 0;
         if (const char* o = getenv("APRIL_B200_OVERLAP")) { overlap_search = atoi(o) > 0; if (atoi(o) > 1) overlap_chunks = std::min(atoi(o), 8); }
         profile = getenv("APRIL_B200_TIMING") != nullptr;
         if (d.D % 16 || d.H % 16 || d.F % 16 || d.J % 16 || (d.C3 * d.F3) % 16) { err = "model dims must be multiples of 16"; return false; }
@@ -783,16 +786,32 @@ public:
         CUtensorMap mAh = make_map_f16(a_hi, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM), mAl = make_map_f16(a_lo, (uint64_t)M, (uint64_t)w.K, tc::GEMM_BM);
         const uint32_t bbox = pair ? tc::GEMM_BN / 2 : tc::GEMM_BN;
         CUtensorMap mBh = make_map_f16(w.hi, (uint64_t)w.N, (uint64_t)w.K, bbox), mBl = make_map_f16(w.lo, (uint64_t)w.N, (uint64_t)w.K, bbox);
-        tc::GemmArgs g{ M, w.N, w.K, w.inv_scale, bias, residual, out_f32, out_hi, out_lo };
+        tc::GemmArgs g{ M, w.N, w.K, w.inv_scale, bias, residual, out_f32, out_hi, out_lo, 1, nullptr };
+        // Few tiles (a streaming tick is M = sessions rows): a tile's CTA streaming ALL of K is paced by what one SM ingests (FF2 at
+        // M = 256: 2 work items, 46 us) while the rest of the GPU idles. Cut K into ranges of >= 2 k-blocks so that the work items
+        // about fill the GPU; the partial tiles are summed in order by a second small kernel (deterministic, unlike atomics).
+        const int nkb = (w.K + tc::GEMM_BK - 1) / tc::GEMM_BK;
+        const int work = pair ? ((tiles_m + 1) / 2) * tiles_n : tiles_m * tiles_n, units = pair ? sm_budget / 2 : sm_budget;
+        if (splitk_ok && work * 2 <= units && nkb >= 4) {
+            g.ksplit = std::max(1, std::min({ nkb / 2, units / work, 16 }));
+            if (g.ksplit > 1) { b_splitk.ensure(sizeof(float) * (size_t)g.ksplit * M * w.N); g.partial = b_splitk.as<float>(); } else g.ksplit = 1;
+        }
         if (pair) {
-            const int work = ((tiles_m + 1) / 2) * tiles_n;
-            const unsigned grid = 2u * (unsigned)std::min(work, sm_budget / 2);
+            const unsigned grid = 2u * (unsigned)std::min(work * g.ksplit, sm_budget / 2);
             if (npass == 3) gemm_tc_epi<3, 2>(epi, grid, mAh, mAl, mBh, mBl, g); else gemm_tc_epi<1, 2>(epi, grid, mAh, mAl, mBh, mBl, g);
         } else {
-            const unsigned grid = (unsigned)std::min(tiles_m * tiles_n, sm_budget);
+            const unsigned grid = (unsigned)std::min(work * g.ksplit, sm_budget);
             if (npass == 3) gemm_tc_epi<3, 1>(epi, grid, mAh, mAl, mBh, mBl, g); else gemm_tc_epi<1, 1>(epi, grid, mAh, mAl, mBh, mBl, g);
         }
         launch_check();
+        if (g.ksplit > 1) {
+            const unsigned fgrid = (unsigned)std::min<size_t>(((size_t)M * w.N / 4 + 255) / 256, (size_t)num_sms * 8);
+            if (epi == tc::GE_F32) tc::gemm_splitk_finish_kernel<tc::GE_F32><<<fgrid, 256, 0, st>>>(g);
+            else if (epi == tc::GE_F32_RESIDUAL) tc::gemm_splitk_finish_kernel<tc::GE_F32_RESIDUAL><<<fgrid, 256, 0, st>>>(g);
+            else if (epi == tc::GE_F32_RESIDUAL_SPLIT) tc::gemm_splitk_finish_kernel<tc::GE_F32_RESIDUAL_SPLIT><<<fgrid, 256, 0, st>>>(g);
+            else tc::gemm_splitk_finish_kernel<tc::GE_DSWISH_SPLIT><<<fgrid, 256, 0, st>>>(g);
+            launch_check();
+        }
         span_end();
     }
 

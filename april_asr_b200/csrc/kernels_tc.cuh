@@ -169,6 +169,8 @@ struct GemmArgs {
     float* out_f32;           // [M,N]
     __half* out_hi;           // [M,N]
     __half* out_lo;
+    int ksplit;               // > 1: K is cut into `ksplit` ranges of k-blocks, one work item each; the raw fp32 partial tiles go to
+    float* partial;           //      partial[ks][M][N] and gemm_splitk_finish_kernel sums them IN ORDER and applies the epilogue
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 256, GEMM_BK = 64;
@@ -212,9 +214,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     // (past the last tile for odd tiles_m: its A loads are zero-filled by TMA and its epilogue stores nothing)
     const int rank = CL == 2 ? (int)cluster_rank_tc() : 0;
     const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
-    const int num_work = ((tiles_m + CL - 1) / CL) * tiles_n;
-    auto work_m0 = [&](int w) { return ((w / tiles_n) * CL + rank) * GEMM_BM; };
-    auto work_n0 = [&](int w) { return (w % tiles_n) * GEMM_BN; };
+    // split-K (small M: a handful of tiles cannot occupy the GPU, and one CTA streaming all of K is paced by what an SM ingests):
+    // work item w = (tile, k-range ks); the ranges of one tile are consecutive work items, so neighbouring CTAs share the A rows in L2
+    const int ksplit = g.ksplit > 1 ? g.ksplit : 1;
+    const int num_work = ((tiles_m + CL - 1) / CL) * tiles_n * ksplit;
+    auto work_m0 = [&](int w) { return (((w / ksplit) / tiles_n) * CL + rank) * GEMM_BM; };
+    auto work_n0 = [&](int w) { return ((w / ksplit) % tiles_n) * GEMM_BN; };
+    auto work_kb0 = [&](int w) { return (int)(((long long)(w % ksplit) * nkb) / ksplit); };
+    auto work_kb1 = [&](int w) { return (int)(((long long)(w % ksplit + 1) * nkb) / ksplit); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -239,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             uint32_t it = 0;
             for (int w = cid; w < num_work; w += ncl) {
                 const int m0 = work_m0(w), n0 = work_n0(w) + rank * (GEMM_BN / CL);   // pair: my half of the B rows
-                for (int kb = 0; kb < nkb; kb++, it++) {
+                for (int kb = work_kb0(w), kbe = work_kb1(w); kb < kbe; kb++, it++) {
                     const int s = it % S; const uint32_t ph = (it / S) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);               // pair: the leader's commit is multicast to both CTAs
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
@@ -277,14 +284,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 mbar_wait(tempty_bar(acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
-                for (int kb = 0; kb < nkb; kb++, it++) {
+                const int kbs = work_kb0(w);
+                for (int kb = kbs, kbe = work_kb1(w); kb < kbe; kb++, it++) {
                     const int s = it % S; const uint32_t ph = (it / S) & 1;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
                     const uint64_t ahi = make_sw128_desc(st), bhi = make_sw128_desc(st + Cfg::A_BYTES);
                     const uint64_t alo = make_sw128_desc(st + Cfg::A_BYTES + Cfg::B_BYTES), blo = make_sw128_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
-                    const uint32_t first = kb != 0;
+                    const uint32_t first = kb != kbs;
                     if (elect_one()) {
                         auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) { if (CL == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum); else umma_f16(d_tmem, ad, bd, idesc, accum); };
                         if (NPASS == 3) {
@@ -322,7 +330,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 if (nb >= g.N) break;                      // warp-uniform
                 float v[32];
                 tmem_ld32(tmem_base + acc * GEMM_BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
-                if (m < g.M) {
+                if (m < g.M && ksplit > 1) {                                 // raw partial sums of this k-range
+                    float* pw = g.partial + ((size_t)(w % ksplit) * g.M + m) * g.N + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (nb + j < g.N) *reinterpret_cast<float4*>(pw + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else if (m < g.M) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         if (nb + j >= g.N) break;
@@ -363,6 +376,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     __syncthreads();
     if (CL == 2) cluster_sync_tc();                        // no exit while the peer may still read my operands or signal my barriers
     if (warp == 1) { if (CL == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+}
+
+// split-K second half: out = epilogue((partial[0] + partial[1] + ... in this order) * inv_scale + bias); 4 columns per thread
+template <int EPI>
+__global__ void gemm_splitk_finish_kernel(GemmArgs g) {
+    const size_t total4 = (size_t)g.M * g.N / 4, plane = (size_t)g.M * g.N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t off = i * 4;
+        const int n = (int)(off % (size_t)g.N);
+        float4 a = *reinterpret_cast<const float4*>(g.partial + off);
+        for (int ks = 1; ks < g.ksplit; ks++) {
+            const float4 b = *reinterpret_cast<const float4*>(g.partial + (size_t)ks * plane + off);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        float x[4] = { a.x * g.inv_scale, a.y * g.inv_scale, a.z * g.inv_scale, a.w * g.inv_scale };
+        if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n)); x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w; }
+        if (EPI == GE_F32 || EPI == GE_F32_RESIDUAL || EPI == GE_F32_RESIDUAL_SPLIT) {
+            if (EPI == GE_F32_RESIDUAL || EPI == GE_F32_RESIDUAL_SPLIT) {
+                const float4 r = *reinterpret_cast<const float4*>(g.residual + off);
+                x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
+            }
+            *reinterpret_cast<float4*>(g.out_f32 + off) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) x[e] = dswish_f(x[e]);
+        }
+        if (EPI == GE_F32_RESIDUAL_SPLIT || EPI == GE_DSWISH_SPLIT) {
+            __align__(8) __half hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) split_f16(x[e], hi[e], lo[e]);
+            *reinterpret_cast<uint2*>(g.out_hi + off) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(g.out_lo + off) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -27,7 +27,10 @@ def run(model, tier, a, w, b):
     return out
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 64, 64), (1000, 512, 2304), (777, 264, 144), (4096, 4096, 512), (49664 // 8, 2048, 512)])
+# (256, 512, 2048), (64, 4096, 512), (1000, 512, 2304): few tiles and a long K, the engine cuts K into ranges (split-K, CTA pairs and single
+# CTAs) and sums the partial tiles in a second kernel
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 64, 64), (1000, 512, 2304), (777, 264, 144), (4096, 4096, 512), (49664 // 8, 2048, 512),
+                                   (256, 512, 2048), (64, 4096, 512), (300, 1024, 1024)])
 def test_gemm_tiers(model, M, N, K):
     rs = np.random.RandomState(M + N + K)
     a = (rs.randn(M, K) * rs.choice([0.01, 1.0, 30.0], size=(M, 1))).astype(np.float32)
