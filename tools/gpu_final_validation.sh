@@ -2,7 +2,7 @@
 # Round 2, final validation on one GPU: smoke, the GPU suite, the default bench line (+ b512, stream, cpu_baseline blocks), the reference
 # arm, the streaming mode, and the ncu launch list of the default command.
 set -u
-O=gpurun_out/r2u; mkdir -p $O
+O=gpurun_out/r3c; mkdir -p $O
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
 timeout 1800 python -m pytest tests -m gpu -q --durations=8 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -14 $O/pytest_gpu.log
 timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "bench rc=$?"; cut -c1-300 $O/bench_default.json
