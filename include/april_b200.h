@@ -6,10 +6,10 @@
  * (fbank -> encoder -> decoder/joiner -> greedy search) over many sessions; these entry points
  * expose that batching for SYNCHRONOUS sessions without changing any reference type: the session
  * handles, AprilConfig, the handler and its calling convention are exactly april_api.h's.
- * Semantics: identical to calling aas_feed_pcm16 / aas_flush on each session in index order —
- * every session's handler runs on the caller's thread before the call returns, session i's
- * callbacks complete before session i+1's start — but all sessions advance through ONE batched
- * device pass. Plain pointers and sizes only.
+ * Semantics: what calling aas_feed_pcm16 / aas_flush on each session would do — every session's
+ * handler runs on the caller's thread before the call returns and sees that session's callbacks
+ * in stream order (the order ACROSS sessions is described at aab_feed_pcm16_batch) — but all
+ * sessions advance through ONE batched device pass. Plain pointers and sizes only.
  *
  * Reference-side binding a maintainer would add: see INTEGRATION.md.
  */
