@@ -101,7 +101,7 @@ greedy_pair_kernel(JoinerParams P, const float* __restrict__ dtab, const float* 
         if (threadIdx.x < ns) { st[threadIdx.x] = gstate[slot[s0 + threadIdx.x]]; s_newctx[threadIdx.x] = 1; s_n[threadIdx.x] = nsteps[s0 + threadIdx.x]; }
     }
     __syncthreads();
-    cluster_sync_all();                                    // the peer's barriers exist before anyone signals them (all 288 threads, once)
+    cluster_sync_all();                                    // the peer's barriers exist before anyone signals them
 
     // stage n of the row stream = rows (n mod nst) * 32 ... of my half, into buffer n mod 2 (called by thread 0 only)
     auto issue_stage = [&](uint32_t n) {
@@ -113,7 +113,6 @@ greedy_pair_kernel(JoinerParams P, const float* __restrict__ dtab, const float* 
         gp_bulk_g2s(tc::smem_u32(wst + (size_t)sb * GP_ROWS * J), P.join_w + (size_t)r0 * J, bytes, full_bar(sb));
     };
     {
-        // ===================== consumers =====================
         int t_end = 0;
         for (int s = 0; s < ns; s++) t_end = max(t_end, min(s_n[s], t_base + chunk_T));
         const uint32_t ebytes = (uint32_t)ns * (uint32_t)J * 4u;
